@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the hot path (BASELINE.json: "MSDeformAttn fwd+bwd GB/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + one backward of the MSDA encoder op over one synthetic batch of
+BASELINE.json configs[1]: 800x1333 pyramid (4 levels, S = Nq = 22323), 256-d, 8 heads, 4 points,
+batch 8 per GPU, fp32.  With N > 1 every rank owns its own 8 images (the path shards by image, no
+collective on the data path => weak scaling); the value is all ranks' algorithmic bytes over the
+slowest rank's time.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (backward), algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
+  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
+  extra         the other measured variants (loc distributions, bf16, decoder shapes, relation op)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MSDeformAttn fwd+bwd GB/s"
+UNIT = "GB/s"
+WORKLOAD = "msda_enc_800x1333_b8"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, p in zip(names, parts[2:6]):
+                if p.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path (grid_sample + autograd)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_step(inp):
+    """One fwd+bwd of the reference's CPU path (oracle/torch_port.py; autograd backward as upstream)."""
+    import torch
+    from oracle import torch_port
+
+    v = inp["value"].detach().requires_grad_(True)
+    loc = inp["sampling_locations"].detach().requires_grad_(True)
+    attn = inp["attention_weights"].detach().requires_grad_(True)
+    out = torch_port.msda_grid_sample(v, inp["spatial_shapes"], loc, attn)
+    out.backward(inp["grad_output"])
+    return out
+
+
+def time_cpu_port(steps: int, warmup: int, sample_batch: int = 1, loc_kind: str = "S"):
+    """Times the port on a bounded sample (batch `sample_batch` of the same workload) on all host threads."""
+    import torch
+    from relation_detr_b200 import workloads
+
+    full = workloads.MSDA_SHAPES[WORKLOAD]
+    shape = workloads.MsdaShape(full.name, sample_batch, full.levels, 0)
+    inp = workloads.make_msda_inputs(shape, loc_kind, seed=0, device="cpu")
+    for _ in range(warmup):
+        cpu_port_step(inp)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(inp)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    fwd, bwd = shape.algorithmic_bytes(4)
+    cores = torch.get_num_threads()
+    return (fwd + bwd) / dt / 1e9, dt * 1e3, cores, f"batch {sample_batch} of {WORKLOAD} (1/{full.batch} of one step), loc {loc_kind}, fp32, {steps} timed passes"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    import torch
+
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    gbs, ms, cores, sample = time_cpu_port(steps, warmup, 1, args.loc)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "loc": args.loc, "note": "reference CPU path (grid_sample + autograd) via oracle/torch_port.py; each step = bounded sample"},
+        "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "torch_threads": cores, "host_cpus": len(os.sched_getaffinity(0)),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def time_msda(torch, ops, inp, steps, warmup, dtype):
+    """-> (ms_per_step, fwd_ms, bwd_ms) with CUDA events on the current stream; inputs resident in HBM."""
+    v = inp["value"].to(dtype)
+    go = inp["grad_output"].to(dtype)
+    ss, lsi, loc, attn = inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"]
+    for _ in range(warmup):
+        ops.msda_forward(v, ss, lsi, loc, attn)
+        ops.msda_backward(v, ss, lsi, loc, attn, go)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    for i in range(steps):
+        ev[i][0].record()
+        ops.msda_forward(v, ss, lsi, loc, attn)
+        ev[i][1].record()
+        ops.msda_backward(v, ss, lsi, loc, attn, go)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    total = ev[0][0].elapsed_time(ev[-1][2]) / steps
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    return total, fwd, bwd
+
+
+def time_e2e(torch, rd, inp, steps, warmup):
+    """Public API (MultiScaleDeformableAttnFunction.apply + autograd) with pinned host buffers:
+    H2D of value/loc/attn/grad_out and D2H of out + the three gradients inside the timed region."""
+    dev = inp["value"].device
+    host = {k: inp[k].cpu().pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
+    ss, lsi = inp["spatial_shapes"], inp["level_start_index"]
+    res_host = None
+    h2d = sum(t.numel() * t.element_size() for t in host.values())
+
+    def step():
+        nonlocal res_host
+        v = host["value"].to(dev, non_blocking=True).requires_grad_(True)
+        loc = host["sampling_locations"].to(dev, non_blocking=True).requires_grad_(True)
+        attn = host["attention_weights"].to(dev, non_blocking=True).requires_grad_(True)
+        go = host["grad_output"].to(dev, non_blocking=True)
+        out = rd.MultiScaleDeformableAttnFunction.apply(v, ss, lsi, loc, attn, 64)
+        out.backward(go)
+        outs = (out.detach(), v.grad, loc.grad, attn.grad)
+        if res_host is None:
+            res_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs]
+        for h, t in zip(res_host, outs):
+            h.copy_(t, non_blocking=True)
+        return sum(t.numel() * t.element_size() for t in outs)
+
+    d2h = 0
+    for _ in range(warmup):
+        d2h = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        d2h = step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, h2d, d2h
+
+
+def time_rel(torch, ops, wl, name, steps, warmup, fast):
+    shape = wl.REL_SHAPES[name]
+    r = wl.make_rel_inputs(shape, seed=0, device="cuda")
+    dim_t = ops.relation_dim_t(16, 10000.0, "cuda")
+    args = (r["src_boxes"], r["tgt_boxes"], r["weight"], r["bias"], dim_t, 100.0, 1e-5, None, fast)
+    for _ in range(warmup):
+        out, bits = ops.relation_forward(*args)
+        ops.relation_backward(r["src_boxes"], r["tgt_boxes"], dim_t, 100.0, 1e-5, r["grad_output"], bits, 8, fast)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    for i in range(steps):
+        ev[i][0].record()
+        out, bits = ops.relation_forward(*args)
+        ev[i][1].record()
+        ops.relation_backward(r["src_boxes"], r["tgt_boxes"], dim_t, 100.0, 1e-5, r["grad_output"], bits, 8, fast)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    fb, bb = shape.algorithmic_bytes()
+    return {"fwd_ms": round(fwd, 4), "bwd_ms": round(bwd, 4), "fwd_GBps": round(fb / fwd / 1e6, 1), "bwd_GBps": round(bb / bwd / 1e6, 1)}
+
+
+def run_ours(args):
+    import torch
+
+    import relation_detr_b200 as rd
+    from relation_detr_b200 import dist as rdist
+    from relation_detr_b200 import ops, workloads
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: relation-detr_b200 has no CPU path (use --impl reference for the CPU arm)")
+    rank, local_rank, world = rdist.env_rank_world()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        rdist.init_process_group("nccl")
+    dev = torch.device("cuda", local_rank)
+    peak, peak_src = measured_peak()
+
+    shape = workloads.MSDA_SHAPES[WORKLOAD]
+    dtype = torch.float32
+    # every rank owns its own images: seed differs per rank, shapes are identical (weak scaling)
+    inp = workloads.make_msda_inputs(shape, args.loc, seed=rank, device=dev)
+    fwd_b, bwd_b = shape.algorithmic_bytes(4)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rdist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    ms, fwd_ms, bwd_ms = time_msda(torch, ops, inp, args.steps, args.warmup, dtype)
+    torch.cuda.synchronize()
+    rdist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_max = rdist.max_over_ranks(ms, dev)
+    fwd_max = rdist.max_over_ranks(fwd_ms, dev)
+    bwd_max = rdist.max_over_ranks(bwd_ms, dev)
+    value = world * (fwd_b + bwd_b) / ms_max / 1e6  # GB/s, whole job
+
+    # e2e through the public API with host buffers (fewer steps: PCIe-bound)
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms, h2d, d2h = time_e2e(torch, rd, inp, e2e_steps, 1)
+    e2e_ms_max = rdist.max_over_ranks(e2e_ms, dev)
+    e2e_value = world * (fwd_b + bwd_b) / e2e_ms_max / 1e6
+
+    extra = {}
+    cpu_baseline = None
+    if rank == 0 and not args.quick:
+        k, w = max(3, min(args.steps, 10)), 3
+        other = "U" if args.loc == "S" else "S"
+        inp_o = workloads.make_msda_inputs(shape, other, seed=0, device=dev)
+        t, f, b = time_msda(torch, ops, inp_o, k, w, torch.float32)
+        extra[f"msda_enc_b8_f32_loc{other}"] = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((fwd_b + bwd_b) / t / 1e6, 1)}
+        f16, b16 = shape.algorithmic_bytes(2)
+        for kind, data in ((args.loc, inp), (other, inp_o)):
+            t, f, b = time_msda(torch, ops, data, k, w, torch.bfloat16)
+            extra[f"msda_enc_b8_bf16_loc{kind}"] = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((f16 + b16) / t / 1e6, 1)}
+        del inp_o
+        for name, kind in (("msda_dec_900_b8", "D"), ("msda_dec_1500_b8", "D"), ("msda_enc_1200x2000_b1", "S")):
+            s2 = workloads.MSDA_SHAPES[name]
+            d2 = workloads.make_msda_inputs(s2, kind, seed=0, device=dev)
+            t, f, b = time_msda(torch, ops, d2, k, w, torch.float32)
+            fb2, bb2 = s2.algorithmic_bytes(4)
+            extra[f"{name}_f32_loc{kind}"] = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((fb2 + bb2) / t / 1e6, 1)}
+            del d2
+        for name in ("rel_900_b8", "rel_1100_b8"):
+            extra[name + "_exact"] = time_rel(torch, ops, workloads, name, k, w, False)
+            extra[name + "_fast"] = time_rel(torch, ops, workloads, name, k, w, True)
+    if rank == 0 and not args.no_cpu_baseline:
+        gbs, cms, cores, sample = time_cpu_port(3, 1, 1, args.loc)
+        cpu_baseline = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": round(cms, 2)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "loc": args.loc, "batch_per_gpu": shape.batch, "S": shape.S, "Nq": shape.Nq, "heads": 8,
+                       "head_dim": 32, "levels": 4, "points": 4, "parallelism": f"dp{world} (images sharded, no data-path collective)",
+                       "l2": "inputs (640 MB fwd / 1097 MB bwd) exceed the 126 MB L2; no flush needed"},
+            "roofline": {"bound": "hbm", "kernel": "msda_bwd_kernel<float,32> (+ grad_value zero-fill memset, both inside rdetr_msda_backward)",
+                         "achieved": round(bwd_b / bwd_max / 1e6, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(bwd_b / bwd_max / 1e6 / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
+                         "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4)},
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "MultiScaleDeformableAttnFunction.apply + autograd, pinned host buffers"},
+            "gpu_launches": 2 * args.steps, "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--loc", choices=["S", "U"], default="S", help="sampling-location distribution (S = encoder-realistic, U = uniform)")
+    ap.add_argument("--quick", action="store_true", help="skip the extra variants")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,133 @@
+/*
+ * rdetr_ops.h -- C ABI of librdetr_ops.so, the sm_100a implementation of the Relation-DETR hot path.
+ *
+ * These entry points are what the reference's native binding for this path would bind instead of
+ * its pybind11 module `MultiScaleDeformableAttention`
+ *   (upstream models/bricks/ops/cuda/ms_deform_attn_cuda.cu:148-151:
+ *    ms_deform_attn_forward / ms_deform_attn_backward),
+ * plus a fused replacement for the eager PositionRelationEmbedding.forward
+ *   (upstream models/bricks/relation_transformer.py:520-532), which has no native code upstream.
+ *
+ * Conventions (all functions):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer on the device that owns
+ *     `value` / `src_boxes` unless the name ends in `_host`;
+ *   - the caller owns every buffer; the library never allocates device memory, never synchronises
+ *     the device and only enqueues work on the stream it is given (cudaStream_t passed as void*);
+ *   - return value 0 = success, otherwise one of RDETR_ERR_*; rdetr_last_error() returns a
+ *     thread-local, human-readable description of the last failure on the calling thread;
+ *   - re-entrant: no global mutable state besides that thread-local message, so forward may run on
+ *     the Python thread while backward runs on the autograd thread;
+ *   - no fallback: an unsupported shape or dtype returns RDETR_ERR_UNSUPPORTED.
+ */
+#ifndef RDETR_OPS_H_
+#define RDETR_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDETR_ABI_VERSION 1
+
+#define RDETR_OK 0
+#define RDETR_ERR_INVALID_ARGUMENT 1 /* null pointer, non-positive size, misaligned buffer */
+#define RDETR_ERR_UNSUPPORTED 2      /* shape / dtype outside what the kernels are built for */
+#define RDETR_ERR_CUDA 3             /* a CUDA runtime call or the launch itself failed */
+#define RDETR_ERR_WORKSPACE 4        /* workspace missing or smaller than *_workspace_bytes() */
+
+/* value_dtype: element type of value / out / grad_out / grad_value.  sampling locations,
+ * attention weights and their gradients are always fp32. */
+#define RDETR_DTYPE_F32 0
+#define RDETR_DTYPE_BF16 1
+
+/* flags for the relation kernels */
+#define RDETR_REL_EXACT 0 /* evaluation order of the reference: (e*scale)/dim_t, sinf/cosf, true division */
+#define RDETR_REL_FAST 1  /* restructured arithmetic, looser documented bound */
+
+typedef void *rdetr_stream_t; /* a cudaStream_t */
+
+int rdetr_abi_version(void);
+const char *rdetr_last_error(void);
+
+/*
+ * Multi-scale deformable attention, forward.
+ * Replaces ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:12-72) and the kernel it launches
+ * (ms_deform_im2col_cuda.cuh:226-288).  `im2col_step` of the reference has no equivalent: the whole
+ * batch is one launch.
+ *
+ *   value               [B, S, M, D]        value_dtype, contiguous, 16-byte aligned
+ *   spatial_shapes      [L, 2] int64 (h, w) device memory, read inside the kernel
+ *   level_start_index   [L]    int64        device memory, read inside the kernel
+ *   sampling_locations  [B, Nq, M, L, P, 2] fp32, last dim (x, y) normalised to [0, 1]
+ *   attention_weights   [B, Nq, M, L, P]    fp32
+ *   out                 [B, Nq, M*D]        value_dtype; every element is written
+ * Supported: D == 32, 1 <= L <= 8, 1 <= P <= 8, S*M*D < 2^31.
+ */
+int rdetr_msda_forward(const void *value, const int64_t *spatial_shapes,
+                       const int64_t *level_start_index, const float *sampling_locations,
+                       const float *attention_weights, void *out, int B, int S, int M, int D, int L,
+                       int Nq, int P, int value_dtype, rdetr_stream_t stream);
+
+/*
+ * Multi-scale deformable attention, backward.
+ * Replaces ms_deform_attn_cuda_backward (ms_deform_attn_cuda.cu:75-145) and
+ * ms_deformable_col2im_gpu_kernel_* (ms_deform_im2col_cuda.cuh:290-909).
+ *
+ *   grad_out   [B, Nq, M*D]         value_dtype
+ *   grad_value [B, S, M, D]         value_dtype; ZEROED INSIDE this call, then accumulated
+ *   grad_loc   [B, Nq, M, L, P, 2]  fp32; every element is written (0 for samples outside the map)
+ *   grad_attn  [B, Nq, M, L, P]     fp32; every element is written
+ *   workspace  rdetr_msda_backward_workspace_bytes() bytes of device scratch (may be NULL when that
+ *              returns 0); contents are undefined on return.
+ */
+size_t rdetr_msda_backward_workspace_bytes(int B, int S, int M, int D, int L, int Nq, int P,
+                                           int value_dtype);
+int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes,
+                        const int64_t *level_start_index, const float *sampling_locations,
+                        const float *attention_weights, const void *grad_out, void *grad_value,
+                        float *grad_loc, float *grad_attn, int B, int S, int M, int D, int L, int Nq,
+                        int P, int value_dtype, void *workspace, size_t workspace_bytes,
+                        rdetr_stream_t stream);
+
+/*
+ * Fused position-relation embedding, forward:
+ *   out[b,h,i,j] = relu(bias[h] + sum_n weight[h,n] * f_n(src[b,i], tgt[b,j]))
+ * with f = sin/cos encoding of the 4 log-ratio box features
+ * (relation_transformer.py:481-490, 520-532; position_encoding.py:131-138).  The [B,N1,N2,64]
+ * intermediate is never materialised.
+ *
+ *   src_boxes  [B, N1, 4] fp32 cxcywh     tgt_boxes [B, N2, 4] fp32 (may alias src_boxes)
+ *   weight     [H, 64]    fp32 (= pos_proj.0.weight viewed 2-D)     bias [H] fp32
+ *   dim_t      [8]        fp32 DEVICE pointer, temperature ** (2k/16) as torch computed it
+ *   attn_mask  NULL or [N1, N2] bytes (torch.bool); non-zero => out = -inf (the decoder's
+ *              masked_fill_, relation_transformer.py:372-374, fused)
+ *   out        [B, H, N1, N2] fp32
+ *   relu_bits  NULL or [B, H, N1, ceil(N2/32)] uint32; bit (j%32) of word j/32 = pre-activation > 0.
+ *              Needed by the backward because the caller mutates `out` in place.
+ * Supported: H == 8, 64 input features (num_pos_feats 16 x 4 box features).
+ */
+int rdetr_relation_forward(const float *src_boxes, const float *tgt_boxes, const float *weight,
+                           const float *bias, const float *dim_t, float scale, float eps,
+                           const uint8_t *attn_mask, float *out, uint32_t *relu_bits, int B, int N1,
+                           int N2, int H, int flags, rdetr_stream_t stream);
+
+/*
+ * Fused position-relation embedding, backward (parameters only; boxes carry no gradient because
+ * the reference computes the geometry under no_grad, relation_transformer.py:527-529):
+ *   G = grad_out * relu_bits;  grad_weight[h,n] = sum_{b,i,j} G * f_n;  grad_bias[h] = sum G
+ *
+ *   grad_out    [B, H, N1, N2] fp32
+ *   relu_bits   as written by the forward (required)
+ *   grad_weight [H, 64] fp32, grad_bias [H] fp32: ZEROED INSIDE this call, then accumulated
+ */
+int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, const float *dim_t,
+                            float scale, float eps, const float *grad_out,
+                            const uint32_t *relu_bits, float *grad_weight, float *grad_bias, int B,
+                            int N1, int N2, int H, int flags, rdetr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDETR_OPS_H_ */

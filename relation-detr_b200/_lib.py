@@ -1,0 +1,60 @@
+"""ctypes binding of ``librdetr_ops.so`` (the C ABI declared in ``include/rdetr_ops.h``).
+
+There is no CPU path and no fallback: if the library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("RDETR_OPS_LIB", os.path.join(PKG_DIR, "librdetr_ops.so"))
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+REL_EXACT, REL_FAST = 0, 1
+
+# every symbol include/rdetr_ops.h declares: name -> (restype, argtypes)
+_SIGNATURES = {
+    "rdetr_abi_version": (c_int, []),
+    "rdetr_last_error": (c_char_p, []),
+    "rdetr_msda_forward": (c_int, [c_void_p] * 6 + [c_int] * 8 + [c_void_p]),
+    "rdetr_msda_backward_workspace_bytes": (c_size_t, [c_int] * 8),
+    "rdetr_msda_backward": (c_int, [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
+    "rdetr_relation_forward": (c_int, [c_void_p] * 5 + [c_float, c_float] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
+    "rdetr_relation_backward": (c_int, [c_void_p] * 3 + [c_float, c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class RdetrOpsError(RuntimeError):
+    """A C-ABI call returned non-zero (the reference only printf's launch errors, cuh:937-941)."""
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: build it with `python -m relation_detr_b200.build` "
+                        "(nvcc, sm_100a). relation-detr_b200 has no CPU or PyTorch fallback."
+                    )
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)  # AttributeError if the .so does not export it
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().rdetr_last_error()
+        raise RdetrOpsError(f"{what} failed (code {rc}): {msg.decode(errors='replace') if msg else ''}")

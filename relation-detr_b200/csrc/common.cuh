@@ -1,0 +1,158 @@
+// common.cuh -- shared device helpers and host-side error plumbing for librdetr_ops.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rdetr_ops.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "librdetr_ops is written for sm_100a (B200) only"
+#endif
+
+namespace rdetr {
+
+// ---- host side ---------------------------------------------------------------------------------
+int fail(int code, const char *fmt, ...);  // records the thread-local message, returns `code`
+int check_cuda(cudaError_t e, const char *what);
+// Makes the device that owns `ptr` current for this thread (the reference has no device guard,
+// ms_deform_attn_cuda.cu:57; we derive the device from the data so multi-GPU callers are safe).
+int enter_device_of(const void *ptr);
+
+constexpr int kMaxLevels = 8;
+constexpr int kMaxPoints = 8;
+
+// ---- device side -------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// streaming (read-once) loads: keep them out of L1 so gathered value lines stay resident
+__device__ __forceinline__ float2 ld_stream_f2(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f1(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// vector reduction to global memory without a return value: one 16-byte request per lane
+__device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+// bf16 pair packed in a 32-bit word -> two floats (exact: bf16 is the top half of an fp32)
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low half), .y = hi
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+// Per-lane slice of one (pixel, head) row of `value`: 16 bytes = 4 fp32 or 8 bf16 channels.
+template <typename VT>
+struct Slice;
+
+template <>
+struct Slice<float> {
+    static constexpr int kCh = 4;
+    __device__ __forceinline__ static void load(const float *p, float (&v)[4])
+    {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ static void load_stream(const float *p, float (&v)[4])
+    {
+        const float4 t = ld_stream_f4(reinterpret_cast<const float4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ static void store(float *p, const float (&v)[4])
+    {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+template <>
+struct Slice<__nv_bfloat16> {
+    static constexpr int kCh = 8;
+    __device__ __forceinline__ static void unpack(const uint4 t, float (&v)[8])
+    {
+        v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
+        v[4] = bf16lo(t.z); v[5] = bf16hi(t.z); v[6] = bf16lo(t.w); v[7] = bf16hi(t.w);
+    }
+    __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&v)[8])
+    {
+        unpack(__ldg(reinterpret_cast<const uint4 *>(p)), v);
+    }
+    __device__ __forceinline__ static void load_stream(const __nv_bfloat16 *p, float (&v)[8])
+    {
+        unpack(ld_stream_u4(reinterpret_cast<const uint4 *>(p)), v);
+    }
+    __device__ __forceinline__ static void store(__nv_bfloat16 *p, const float (&v)[8])
+    {
+        uint4 t;
+        t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
+        t.z = pack_bf16(v[4], v[5]); t.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+
+// One bilinear tap, prepared once per sample and shared by the lanes that own its channels.
+//   pix[i] : index of the corner's pixel inside the batch element (level_start + h*W + w), -1 if the
+//            corner is outside the level (zero padding) or the sample is outside the validity window
+//   lw, lh : fractional parts; hw = 1-lw, hh = 1-lh
+// Arithmetic follows ms_deform_im2col_cuda.cuh:261-285 and :22-73 of the reference:
+//   w_im = loc_x*W - 0.5, h_im = loc_y*H - 0.5; contributes iff h_im>-1 && w_im>-1 && h_im<H && w_im<W
+struct Tap {
+    int pix[4];
+    float lw, lh;
+};
+
+__device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int start)
+{
+    Tap t;
+    const float w_im = fmaf(lx, (float)W, -0.5f);
+    const float h_im = fmaf(ly, (float)H, -0.5f);
+    const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < (float)H) && (w_im < (float)W);
+    const float h0f = floorf(h_im), w0f = floorf(w_im);
+    const int h0 = (int)h0f, w0 = (int)w0f;
+    const int h1 = h0 + 1, w1 = w0 + 1;
+    t.lh = h_im - h0f;
+    t.lw = w_im - w0f;
+    const bool h0ok = inside && h0 >= 0, h1ok = inside && h1 <= H - 1;
+    const bool w0ok = w0 >= 0, w1ok = w1 <= W - 1;
+    const int base = start + h0 * W + w0;
+    t.pix[0] = (h0ok && w0ok) ? base : -1;
+    t.pix[1] = (h0ok && w1ok) ? base + 1 : -1;
+    t.pix[2] = (h1ok && w0ok) ? base + W : -1;
+    t.pix[3] = (h1ok && w1ok) ? base + W + 1 : -1;
+    if (!inside) { t.lh = 0.f; t.lw = 0.f; }  // NaN / inf locations must not leak into weights
+    return t;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace rdetr

@@ -1,0 +1,247 @@
+// msda_bwd.cu -- multi-scale deformable attention backward for sm_100a.
+//
+// Replaces ms_deformable_col2im_gpu_kernel_shm_blocksize_aware_reduce_v1<float,32> and its five
+// siblings (upstream models/bricks/ops/cuda/ms_deform_im2col_cuda.cuh:290-909): one-warp CTAs, 64
+// scalar global atomics per thread and a serial thread-0 reduction per sample.
+//
+// Same work layout as the forward (see msda_fwd.cu):
+//   * phase 1, one thread per sample: corner pixel indices, fractional offsets and the attention
+//     weight staged in shared memory (32 B per sample);
+//   * phase 2, 16 B of channels per lane, kLanes lanes per (b,q,m): re-gather the four corners,
+//       - grad_value: one vector reduction (red.global.add.v4.f32, 16 B per lane => a whole
+//         128-byte row per corner for fp32) instead of 32 scalar atomics;
+//       - grad_attn / grad_loc: per-lane partial dot products over its channels, combined with
+//         log2(kLanes) xor-shuffles; the results overwrite the sample's shared-memory slot;
+//   * phase 3: grad_loc / grad_attn leave the CTA as dense, coalesced stores (every element is
+//     written, so the caller does not have to zero them; the reference zero-fills and then
+//     overwrites, ms_deform_attn_cuda.cu:113-115).
+// grad_value accumulates in fp32.  For bf16 value the accumulation target is an fp32 workspace that
+// a second kernel converts (bf16 accumulation would lose the small addends on coarse levels, where
+// one address receives ~1e3 updates).
+#include "common.cuh"
+
+namespace rdetr {
+
+int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype);
+
+constexpr int kBwdThreads = 256;
+
+template <typename VT, int D>
+__global__ void __launch_bounds__(kBwdThreads)
+msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
+                const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
+                const float *__restrict__ attn, const VT *__restrict__ grad_out, float *__restrict__ grad_value_f32,
+                float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, int L, int Nq, int P,
+                long long total_pairs)
+{
+    constexpr int kCh = Slice<VT>::kCh;
+    constexpr int kLanes = D / kCh;
+    constexpr int kPairs = kBwdThreads / kLanes;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
+
+    const int LP = L * P;
+    const int stride = LP + 1;
+    int4 *s_pix = reinterpret_cast<int4 *>(smem_raw);                      // [kPairs][stride]
+    float4 *s_meta = reinterpret_cast<float4 *>(s_pix + kPairs * stride);  // in: (lw, lh, attn, -)  out: (gx, gy, ga, -)
+
+    if (threadIdx.x < L) {
+        s_H[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x];
+        s_W[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x + 1];
+        s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
+    }
+    __syncthreads();
+
+    const long long pair0 = (long long)blockIdx.x * kPairs;
+    const long long left = total_pairs - pair0;
+    const int npairs = left < kPairs ? (int)left : kPairs;
+    const int nsamples = npairs * LP;
+
+    // ---- phase 1 -----------------------------------------------------------------------------------
+    const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + pair0 * LP;
+    const float *attn0 = attn + pair0 * LP;
+    for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
+        const int pair = s / LP;
+        const int lp = s - pair * LP;
+        const int l = lp / P;
+        const float2 xy = ld_stream_f2(loc2 + s);
+        const float a = ld_stream_f1(attn0 + s);
+        const Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
+        s_meta[pair * stride + lp] = make_float4(t.lw, t.lh, a, 0.f);
+    }
+    __syncthreads();
+
+    // ---- phase 2 -----------------------------------------------------------------------------------
+    const int pair = threadIdx.x / kLanes;
+    const int lane = threadIdx.x - pair * kLanes;
+    const bool active = pair < npairs;
+    const long long gp = pair0 + (active ? pair : 0);
+    const int m = (int)(gp % M);
+    const long long b = (gp / M) / Nq;
+    const long long batch_off = (b * S * M + m) * (long long)D + lane * kCh;
+    const VT *vbase = value + batch_off;
+    float *gvbase = grad_value_f32 + batch_off;
+    const int pix_stride = M * D;
+
+    float g[kCh];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c) g[c] = 0.f;
+    if (active) Slice<VT>::load_stream(grad_out + gp * D + lane * kCh, g);
+
+    const int4 *my_pix = s_pix + pair * stride;
+    float4 *my_meta = s_meta + pair * stride;
+#pragma unroll 2
+    for (int lp = 0; lp < LP; ++lp) {
+        int4 px = make_int4(-1, -1, -1, -1);
+        float4 mt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            px = my_pix[lp];
+            mt = my_meta[lp];
+        }
+        const float lw = mt.x, lh = mt.y, a = mt.z;
+        const float hw = 1.f - lw, hh = 1.f - lh;
+        float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
+        if (px.x >= 0) Slice<VT>::load(vbase + (long long)px.x * pix_stride, v0);
+        if (px.y >= 0) Slice<VT>::load(vbase + (long long)px.y * pix_stride, v1);
+        if (px.z >= 0) Slice<VT>::load(vbase + (long long)px.z * pix_stride, v2);
+        if (px.w >= 0) Slice<VT>::load(vbase + (long long)px.w * pix_stride, v3);
+
+        const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
+        float p_attn = 0.f, p_gw = 0.f, p_gh = 0.f;
+        float tg[kCh];
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+            tg[c] = g[c] * a;
+            const float bil = fmaf(w3, v3[c], fmaf(w2, v2[c], fmaf(w1, v1[c], w0 * v0[c])));
+            // d(bilinear)/d(w_im) and d/d(h_im), cuh:110-141 of the reference
+            const float dw = fmaf(hh, v1[c] - v0[c], lh * (v3[c] - v2[c]));
+            const float dh = fmaf(hw, v2[c] - v0[c], lw * (v3[c] - v1[c]));
+            p_attn = fmaf(g[c], bil, p_attn);
+            p_gw = fmaf(tg[c], dw, p_gw);
+            p_gh = fmaf(tg[c], dh, p_gh);
+        }
+        // grad_value scatter: one 16-byte vector reduction per lane and corner
+#pragma unroll
+        for (int c0 = 0; c0 < kCh; c0 += 4) {
+            if (px.x >= 0) red_add_f32x4(gvbase + (long long)px.x * pix_stride + c0, w0 * tg[c0], w0 * tg[c0 + 1], w0 * tg[c0 + 2], w0 * tg[c0 + 3]);
+            if (px.y >= 0) red_add_f32x4(gvbase + (long long)px.y * pix_stride + c0, w1 * tg[c0], w1 * tg[c0 + 1], w1 * tg[c0 + 2], w1 * tg[c0 + 3]);
+            if (px.z >= 0) red_add_f32x4(gvbase + (long long)px.z * pix_stride + c0, w2 * tg[c0], w2 * tg[c0 + 1], w2 * tg[c0 + 2], w2 * tg[c0 + 3]);
+            if (px.w >= 0) red_add_f32x4(gvbase + (long long)px.w * pix_stride + c0, w3 * tg[c0], w3 * tg[c0 + 1], w3 * tg[c0 + 2], w3 * tg[c0 + 3]);
+        }
+        // combine the kLanes per-lane partials of this (b,q,m)
+#pragma unroll
+        for (int off = kLanes / 2; off > 0; off >>= 1) {
+            p_attn += __shfl_xor_sync(0xffffffffu, p_attn, off);
+            p_gw += __shfl_xor_sync(0xffffffffu, p_gw, off);
+            p_gh += __shfl_xor_sync(0xffffffffu, p_gh, off);
+        }
+        if (active && lane == 0) my_meta[lp] = make_float4(p_gw, p_gh, p_attn, 0.f);
+    }
+    __syncthreads();
+
+    // ---- phase 3: dense stores of grad_loc / grad_attn ----------------------------------------------
+    float2 *gl2 = reinterpret_cast<float2 *>(grad_loc) + pair0 * LP;
+    float *ga0 = grad_attn + pair0 * LP;
+    for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
+        const int pr = s / LP;
+        const int lp = s - pr * LP;
+        const int l = lp / P;
+        const float4 r = s_meta[pr * stride + lp];
+        gl2[s] = make_float2((float)s_W[l] * r.x, (float)s_H[l] * r.y);
+        ga0[s] = r.z;
+    }
+}
+
+// fp32 accumulation buffer -> bf16 grad_value (8 elements per thread)
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                                          long long n8)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(src) + 2 * i);
+    const float4 b = ld_stream_f4(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+    uint4 t;
+    t.x = pack_bf16(a.x, a.y); t.y = pack_bf16(a.z, a.w);
+    t.z = pack_bf16(b.x, b.y); t.w = pack_bf16(b.z, b.w);
+    reinterpret_cast<uint4 *>(dst)[i] = t;
+}
+
+template <typename VT>
+static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
+                      const void *grad_out, float *gv_f32, float *grad_loc, float *grad_attn, int B, int S, int M, int L,
+                      int Nq, int P, cudaStream_t stream)
+{
+    constexpr int D = 32;
+    constexpr int kLanes = D / Slice<VT>::kCh;
+    constexpr int kPairs = kBwdThreads / kLanes;
+    const long long total_pairs = (long long)B * Nq * M;
+    const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
+    auto kern = msda_bwd_kernel<VT, D>;
+    if (smem > 48 * 1024) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                "cudaFuncSetAttribute(msda_bwd)"))
+            return rc;
+    }
+    const long long grid = (total_pairs + kPairs - 1) / kPairs;
+    if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
+    kern<<<(unsigned)grid, kBwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, loc, attn,
+                                                        static_cast<const VT *>(grad_out), gv_f32, grad_loc, grad_attn, S,
+                                                        M, L, Nq, P, total_pairs);
+    return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
+}
+
+}  // namespace rdetr
+
+extern "C" size_t rdetr_msda_backward_workspace_bytes(int B, int S, int M, int D, int L, int Nq, int P, int value_dtype)
+{
+    (void)L; (void)Nq; (void)P;
+    if (value_dtype == RDETR_DTYPE_BF16) return (size_t)B * S * M * D * sizeof(float);
+    return 0;
+}
+
+extern "C" int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                   const float *sampling_locations, const float *attention_weights, const void *grad_out,
+                                   void *grad_value, float *grad_loc, float *grad_attn, int B, int S, int M, int D, int L,
+                                   int Nq, int P, int value_dtype, void *workspace, size_t workspace_bytes,
+                                   rdetr_stream_t stream)
+{
+    using namespace rdetr;
+    if (int rc = validate_msda("rdetr_msda_backward", B, S, M, D, L, Nq, P, value_dtype)) return rc;
+    if (B == 0) return RDETR_OK;
+    if (!value || !spatial_shapes || !level_start_index || !grad_value)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_backward: null pointer argument");
+    if (Nq > 0 && (!sampling_locations || !attention_weights || !grad_out || !grad_loc || !grad_attn))
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_backward: null pointer argument");
+    if (((uintptr_t)value | (uintptr_t)grad_value | (uintptr_t)grad_out | (uintptr_t)sampling_locations |
+         (uintptr_t)attention_weights | (uintptr_t)grad_loc | (uintptr_t)grad_attn | (uintptr_t)workspace) & 15)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_backward: buffers must be 16-byte aligned");
+    const size_t need = rdetr_msda_backward_workspace_bytes(B, S, M, D, L, Nq, P, value_dtype);
+    if (need && (!workspace || workspace_bytes < need))
+        return fail(RDETR_ERR_WORKSPACE, "rdetr_msda_backward: workspace of %zu bytes required, got %zu", need,
+                    workspace ? workspace_bytes : (size_t)0);
+    if (int rc = enter_device_of(value)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nvalue = (size_t)B * S * M * D;
+    float *acc = value_dtype == RDETR_DTYPE_F32 ? static_cast<float *>(grad_value) : static_cast<float *>(workspace);
+    if (int rc = check_cuda(cudaMemsetAsync(acc, 0, nvalue * sizeof(float), st), "cudaMemsetAsync(grad_value)")) return rc;
+    if (Nq > 0) {
+        int rc;
+        if (value_dtype == RDETR_DTYPE_F32)
+            rc = launch_bwd<float>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                                   grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
+        else
+            rc = launch_bwd<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_locations,
+                                           attention_weights, grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
+        if (rc) return rc;
+    }
+    if (value_dtype == RDETR_DTYPE_BF16) {
+        const long long n8 = (long long)(nvalue / 8);  // D == 32 => divisible
+        f32_to_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(acc, static_cast<__nv_bfloat16 *>(grad_value), n8);
+        return check_cuda(cudaGetLastError(), "f32_to_bf16_kernel launch");
+    }
+    return RDETR_OK;
+}

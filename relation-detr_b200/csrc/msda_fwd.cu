@@ -1,0 +1,169 @@
+// msda_fwd.cu -- multi-scale deformable attention forward for sm_100a.
+//
+// Replaces ms_deformable_im2col_gpu_kernel (upstream models/bricks/ops/cuda/ms_deform_im2col_cuda.cuh:226-288),
+// which uses one thread per output scalar and makes all 32 channel threads of a (b,q,m) re-read the
+// same sampling location / weight and redo the same coordinate arithmetic.
+//
+// Layout of the work here:
+//   * a "pair" is one (b, q, m): its L*P samples are contiguous in sampling_locations and
+//     attention_weights, its D outputs are contiguous in `out`, and consecutive pairs are
+//     contiguous too, so a CTA that owns kPairs consecutive pairs streams three dense blocks;
+//   * phase 1 (one thread per sample): coalesced streaming loads of loc/attn, coordinate
+//     arithmetic done ONCE per sample, corner pixel indices + attention-scaled bilinear weights
+//     staged in shared memory (32 B per sample);
+//   * phase 2 (16 B of channels per lane): kLanes = D*sizeof(VT)/16 lanes own one pair (8 lanes for
+//     fp32, 4 for bf16); every corner is one 16-byte read-only load per lane, i.e. a full 128-byte
+//     (fp32) or 64-byte (bf16) contiguous row per pair, 4 corners x 4 points in flight per lane;
+//     fp32 accumulation in registers, one 16-byte store per lane.
+// No tensor cores: the op is a gather, not a contraction.
+#include "common.cuh"
+
+namespace rdetr {
+
+constexpr int kFwdThreads = 256;
+
+template <typename VT, int D>
+__global__ void __launch_bounds__(kFwdThreads)
+msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
+                const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
+                const float *__restrict__ attn, VT *__restrict__ out, int S, int M, int L, int Nq,
+                int P, long long total_pairs)
+{
+    constexpr int kCh = Slice<VT>::kCh;
+    constexpr int kLanes = D / kCh;
+    constexpr int kPairs = kFwdThreads / kLanes;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
+
+    const int LP = L * P;
+    const int stride = LP + 1;  // one slot of padding de-phases consecutive pairs across banks
+    int4 *s_pix = reinterpret_cast<int4 *>(smem_raw);              // [kPairs][stride]
+    float4 *s_wgt = reinterpret_cast<float4 *>(s_pix + kPairs * stride);  // [kPairs][stride]
+
+    if (threadIdx.x < L) {
+        s_H[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x];
+        s_W[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x + 1];
+        s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
+    }
+    __syncthreads();
+
+    const long long pair0 = (long long)blockIdx.x * kPairs;
+    const long long left = total_pairs - pair0;
+    const int npairs = left < kPairs ? (int)left : kPairs;
+
+    // ---- phase 1: one thread per sample ----------------------------------------------------------
+    const int nsamples = npairs * LP;
+    const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + pair0 * LP;
+    const float *attn0 = attn + pair0 * LP;
+    for (int s = threadIdx.x; s < nsamples; s += kFwdThreads) {
+        const int pair = s / LP;
+        const int lp = s - pair * LP;
+        const int l = lp / P;
+        const float2 xy = ld_stream_f2(loc2 + s);
+        const float a = ld_stream_f1(attn0 + s);
+        const Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        const float hh = 1.f - t.lh, hw = 1.f - t.lw;
+        s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
+        s_wgt[pair * stride + lp] = make_float4(a * (hh * hw), a * (hh * t.lw), a * (t.lh * hw), a * (t.lh * t.lw));
+    }
+    __syncthreads();
+
+    // ---- phase 2: gather ---------------------------------------------------------------------------
+    const int pair = threadIdx.x / kLanes;
+    const int lane = threadIdx.x - pair * kLanes;
+    if (pair >= npairs) return;
+    const long long gp = pair0 + pair;
+    const int m = (int)(gp % M);
+    const long long b = (gp / M) / Nq;
+    const VT *vbase = value + (b * S * M + m) * (long long)D + lane * kCh;
+    const int pix_stride = M * D;
+
+    float acc[kCh];
+#pragma unroll
+    for (int c = 0; c < kCh; ++c) acc[c] = 0.f;
+
+    const int4 *my_pix = s_pix + pair * stride;
+    const float4 *my_wgt = s_wgt + pair * stride;
+#pragma unroll 4
+    for (int lp = 0; lp < LP; ++lp) {
+        const int4 px = my_pix[lp];
+        const float4 w = my_wgt[lp];
+        float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
+        if (px.x >= 0) Slice<VT>::load(vbase + (long long)px.x * pix_stride, v0);
+        if (px.y >= 0) Slice<VT>::load(vbase + (long long)px.y * pix_stride, v1);
+        if (px.z >= 0) Slice<VT>::load(vbase + (long long)px.z * pix_stride, v2);
+        if (px.w >= 0) Slice<VT>::load(vbase + (long long)px.w * pix_stride, v3);
+#pragma unroll
+        for (int c = 0; c < kCh; ++c) {
+            acc[c] = fmaf(w.x, v0[c], acc[c]);
+            acc[c] = fmaf(w.y, v1[c], acc[c]);
+            acc[c] = fmaf(w.z, v2[c], acc[c]);
+            acc[c] = fmaf(w.w, v3[c], acc[c]);
+        }
+    }
+    Slice<VT>::store(out + gp * D + lane * kCh, acc);
+}
+
+template <typename VT>
+static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
+                      const float *attn, void *out, int B, int S, int M, int L, int Nq, int P,
+                      cudaStream_t stream)
+{
+    constexpr int D = 32;
+    constexpr int kLanes = D / Slice<VT>::kCh;
+    constexpr int kPairs = kFwdThreads / kLanes;
+    const long long total_pairs = (long long)B * Nq * M;
+    const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
+    auto kern = msda_fwd_kernel<VT, D>;
+    if (smem > 48 * 1024) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                                "cudaFuncSetAttribute(msda_fwd)"))
+            return rc;
+    }
+    const long long grid = (total_pairs + kPairs - 1) / kPairs;
+    if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_forward: B*Nq*M too large (%lld pairs)", total_pairs);
+    kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, loc, attn,
+                                                        static_cast<VT *>(out), S, M, L, Nq, P, total_pairs);
+    return check_cuda(cudaGetLastError(), "msda_fwd_kernel launch");
+}
+
+int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype)
+{
+    if (B < 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Nq < 0 || P <= 0)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "%s: non-positive size (B=%d S=%d M=%d D=%d L=%d Nq=%d P=%d)", who, B, S, M,
+                    D, L, Nq, P);
+    if (D != 32) return fail(RDETR_ERR_UNSUPPORTED, "%s: head dim D=%d unsupported (kernels are built for D=32)", who, D);
+    if (L > kMaxLevels || P > kMaxPoints)
+        return fail(RDETR_ERR_UNSUPPORTED, "%s: L=%d P=%d unsupported (max %d levels, %d points)", who, L, P, kMaxLevels,
+                    kMaxPoints);
+    if ((long long)S * M * D >= (1LL << 31))
+        return fail(RDETR_ERR_UNSUPPORTED, "%s: S*M*D = %lld does not fit 31 bits", who, (long long)S * M * D);
+    if (value_dtype != RDETR_DTYPE_F32 && value_dtype != RDETR_DTYPE_BF16)
+        return fail(RDETR_ERR_UNSUPPORTED, "%s: value_dtype %d unsupported (0 = f32, 1 = bf16)", who, value_dtype);
+    return RDETR_OK;
+}
+
+}  // namespace rdetr
+
+extern "C" int rdetr_msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                  const float *sampling_locations, const float *attention_weights, void *out, int B,
+                                  int S, int M, int D, int L, int Nq, int P, int value_dtype, rdetr_stream_t stream)
+{
+    using namespace rdetr;
+    if (int rc = validate_msda("rdetr_msda_forward", B, S, M, D, L, Nq, P, value_dtype)) return rc;
+    if (B == 0 || Nq == 0) return RDETR_OK;
+    if (!value || !spatial_shapes || !level_start_index || !sampling_locations || !attention_weights || !out)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_forward: null pointer argument");
+    if (((uintptr_t)value | (uintptr_t)out | (uintptr_t)sampling_locations | (uintptr_t)attention_weights) & 15)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_forward: value/out/loc/attn must be 16-byte aligned");
+    if (int rc = enter_device_of(value)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (value_dtype == RDETR_DTYPE_F32)
+        return launch_fwd<float>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, out, B,
+                                 S, M, L, Nq, P, st);
+    return launch_fwd<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                                     out, B, S, M, L, Nq, P, st);
+}

@@ -1,0 +1,150 @@
+"""Drop-in ``nn.Module`` replacements for the two reference modules on the hot path.
+
+Constructor arguments, parameter names (``sampling_offsets``, ``attention_weights``, ``value_proj``,
+``output_proj``, ``pos_proj.0``) and ``forward`` signatures are those of the reference, so released
+checkpoints load with ``strict=True`` and ``optimizer/param_dict.py`` keeps matching by substring:
+
+* ``MultiScaleDeformableAttention``  -- reference ``models/bricks/ms_deform_attn.py:215-377``
+* ``PositionRelationEmbedding``      -- reference ``models/bricks/relation_transformer.py:493-532``
+
+Only the dispatch changes: the sampling / relation arithmetic goes to the sm_100a kernels through
+``ops.py``; there is no grid_sample or eager fallback.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+
+
+class MultiScaleDeformableAttention(nn.Module):
+    """Multi-scale deformable attention (Deformable-DETR), kernels from ``librdetr_ops.so``."""
+
+    def __init__(self, embed_dim: int = 256, num_levels: int = 4, num_heads: int = 8, num_points: int = 4,
+                 img2col_step: int = 64):
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError("embed_dim must be divisible by num_heads, but got {} and {}".format(embed_dim, num_heads))
+        head_dim = embed_dim // num_heads
+        if head_dim & (head_dim - 1) != 0:
+            warnings.warn("embed_dim // num_heads should be a power of 2 for the deformable attention kernels")
+        self.im2col_step = img2col_step  # accepted for signature parity; the whole batch is one launch
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_levels = num_levels
+        self.num_points = num_points
+        # True: a bf16 value (autocast) is read as bf16 by the kernel, fp32 accumulation, bf16 out.
+        # False: up-cast to fp32 first, exactly as the reference does (ms_deform_attn.py:360).
+        self.native_bf16 = True
+        self.sampling_offsets = nn.Linear(embed_dim, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dim, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dim, embed_dim)
+        self.output_proj = nn.Linear(embed_dim, embed_dim)
+        self.init_weights()
+
+    def init_weights(self):
+        """Same initial state as the reference (ms_deform_attn.py:266-284): zero offset weights, a
+        ring of per-head directions scaled by the point index as offset bias, uniform attention."""
+        nn.init.constant_(self.sampling_offsets.weight.data, 0.0)
+        angle = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        ring = torch.stack([angle.cos(), angle.sin()], -1)
+        ring = ring / ring.abs().max(-1, keepdim=True)[0]
+        ring = ring.view(self.num_heads, 1, 1, 2).repeat(1, self.num_levels, self.num_points, 1)
+        ring = ring * torch.arange(1, self.num_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(ring.reshape(-1))
+        nn.init.constant_(self.attention_weights.weight.data, 0.0)
+        nn.init.constant_(self.attention_weights.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.value_proj.weight.data)
+        nn.init.constant_(self.value_proj.bias.data, 0.0)
+        nn.init.xavier_uniform_(self.output_proj.weight.data)
+        nn.init.constant_(self.output_proj.bias.data, 0.0)
+
+    def forward(self, query: Tensor, reference_points: Tensor, value: Tensor, spatial_shapes: Tensor,
+                level_start_index: Tensor, key_padding_mask: Optional[Tensor]) -> Tensor:
+        """query [B,Nq,C]; reference_points [B,Nq,L,2|4] normalised; value [B,S,C]; spatial_shapes [L,2]
+        (h,w) int64; level_start_index [L]; key_padding_mask [B,S] bool or None -> [B,Nq,C].
+
+        Unlike the reference there is no ``assert spatial_shapes.prod(1).sum() == S`` here: that
+        assert forces a device->host sync on every call (ms_deform_attn.py:313)."""
+        B, Nq, _ = query.shape
+        S = value.shape[1]
+        M, L, P = self.num_heads, self.num_levels, self.num_points
+
+        value = self.value_proj(value)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], float(0))
+        value = value.view(B, S, M, self.embed_dim // M)
+
+        offsets = self.sampling_offsets(query).view(B, Nq, M, L, P, 2)
+        weights = self.attention_weights(query).view(B, Nq, M, L * P).softmax(-1).view(B, Nq, M, L, P)
+
+        if reference_points.shape[-1] == 2:
+            wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+            locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            locations = (reference_points[:, :, None, :, None, :2]
+                         + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+
+        in_dtype = value.dtype
+        if not (self.native_bf16 and in_dtype == torch.bfloat16):
+            value = value.to(torch.float32)
+        out = ops.MultiScaleDeformableAttnFunction.apply(
+            value.contiguous(), spatial_shapes, level_start_index,
+            locations.to(torch.float32).contiguous(), weights.to(torch.float32).contiguous(), self.im2col_step)
+        if out.dtype != in_dtype:
+            out = out.to(in_dtype)
+        return self.output_proj(out)
+
+
+class PositionRelationEmbedding(nn.Module):
+    """Box-pair geometry -> per-head attention bias ``[B, H, N1, N2]`` in one kernel.
+
+    ``pos_proj`` is kept as ``Sequential(Conv2d(4*embed_dim, H, 1), ReLU)`` purely as the parameter
+    container the reference's checkpoints expect (keys ``pos_proj.0.weight`` [H,64,1,1] and
+    ``pos_proj.0.bias``); the convolution is never executed."""
+
+    def __init__(self, embed_dim: int = 256, num_heads: int = 8, temperature: float = 10000.0, scale: float = 100.0,
+                 activation_layer=nn.ReLU, inplace: bool = True):
+        super().__init__()
+        if activation_layer is not nn.ReLU:
+            raise NotImplementedError("the fused relation kernel implements the ReLU activation of the shipped configs only")
+        if embed_dim != 16:
+            raise NotImplementedError(f"the fused relation kernel is built for embed_dim=16 (64 features); got {embed_dim}")
+        self.pos_proj = nn.Sequential(nn.Conv2d(embed_dim * 4, num_heads, kernel_size=1, bias=True), nn.ReLU(inplace=inplace))
+        self.out_channels = num_heads
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.temperature = temperature
+        self.scale = scale
+        self.eps = 1e-5  # box_rel_encoding default (relation_transformer.py:481)
+        self.fast_math = False  # True selects RDETR_REL_FAST (documented looser bound)
+        self._dim_t = {}
+
+    def _dim_t_on(self, device) -> Tensor:
+        key = str(device)
+        if key not in self._dim_t:
+            self._dim_t[key] = ops.relation_dim_t(self.embed_dim, self.temperature, device)
+        return self._dim_t[key]
+
+    def forward(self, src_boxes: Tensor, tgt_boxes: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None) -> Tensor:
+        """src_boxes [B,N1,4], tgt_boxes [B,N2,4] (default: src) -> [B,H,N1,N2], a fresh tensor the
+        caller may mutate.  ``attn_mask`` ([N1,N2] bool, optional, not in the reference signature)
+        fuses the decoder's ``masked_fill_(attn_mask, -inf)``."""
+        if tgt_boxes is None:
+            tgt_boxes = src_boxes
+        torch._assert(src_boxes.shape[-1] == 4, "src_boxes much have 4 coordinates")
+        torch._assert(tgt_boxes.shape[-1] == 4, "tgt_boxes must have 4 coordinates")
+        conv = self.pos_proj[0]
+        out = ops.position_relation_bias(src_boxes, tgt_boxes, conv.weight, conv.bias, self._dim_t_on(src_boxes.device),
+                                         self.scale, self.eps, attn_mask, self.fast_math)
+        if torch.is_autocast_enabled():
+            out = out.to(torch.get_autocast_dtype("cuda"))  # the reference's Conv2d returns the autocast dtype
+        return out

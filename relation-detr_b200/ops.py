@@ -1,0 +1,250 @@
+"""The two hot-path operators as ``torch.library`` custom ops over the C ABI.
+
+Mirrors the reference's operator interface for this path:
+
+* ``MultiScaleDeformableAttnFunction.apply(value, value_spatial_shapes, level_start_index,
+  sampling_locations, attention_weights, im2col_step)`` -- reference
+  ``models/bricks/ms_deform_attn.py:35-84`` (pybind ``_C.ms_deform_attn_forward/backward``,
+  ``ops/cuda/ms_deform_attn_cuda.cu:148-151``).
+* ``position_relation_bias(src_boxes, tgt_boxes, weight, bias, ...)`` -- the fused body of
+  ``PositionRelationEmbedding.forward`` (``models/bricks/relation_transformer.py:520-532``).
+
+PyTorch is plumbing here (device memory, streams, autograd registration); the arithmetic is in
+``csrc/*.cu``.  Nothing in this module computes on the CPU: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+__all__ = [
+    "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
+    "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
+]
+
+
+def _ptr(t: Optional[Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream(t: Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _value_dtype_code(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    if t.dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    raise RuntimeError(f"rdetr::msda: value dtype {t.dtype} unsupported (float32 or bfloat16)")
+
+
+def _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    # same preconditions the reference asserts (ms_deform_attn_cuda.cu:20-30), raised as RuntimeError
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                    ("sampling_loc", sampling_locations), ("attn_weight", attention_weights)):
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    _require(value.dim() == 4, "value must be [B, S, M, D]")
+    _require(sampling_locations.dim() == 6 and sampling_locations.shape[-1] == 2, "sampling_loc must be [B, Nq, M, L, P, 2]")
+    _require(attention_weights.shape == sampling_locations.shape[:-1], "attn_weight must be [B, Nq, M, L, P]")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes / level_start_index must be int64")
+    _require(sampling_locations.dtype == torch.float32 and attention_weights.dtype == torch.float32,
+             "sampling_loc / attn_weight must be float32")
+    B, S, M, D = value.shape
+    Bq, Nq, Mq, L, P, _ = sampling_locations.shape
+    _require(B == Bq and M == Mq, "batch / head mismatch between value and sampling_loc")
+    _require(spatial_shapes.shape == (L, 2) and level_start_index.shape == (L,), "spatial_shapes must be [L, 2], level_start_index [L]")
+    return B, S, M, D, L, Nq, P
+
+
+# ---- MSDA ---------------------------------------------------------------------------------------
+
+@torch.library.custom_op("rdetr::msda_forward", mutates_args=(), device_types="cuda")
+def msda_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_locations: Tensor,
+                 attention_weights: Tensor) -> Tensor:
+    B, S, M, D, L, Nq, P = _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    out = torch.empty((B, Nq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().rdetr_msda_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+                                           _ptr(sampling_locations), _ptr(attention_weights), _ptr(out),
+                                           B, S, M, D, L, Nq, P, _value_dtype_code(value), _stream(value))
+    _lib.check(rc, "rdetr_msda_forward")
+    return out
+
+
+@msda_forward.register_fake
+def _(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    B, _, M, D = value.shape
+    return value.new_empty((B, sampling_locations.shape[1], M * D))
+
+
+@torch.library.custom_op("rdetr::msda_backward", mutates_args=(), device_types="cuda")
+def msda_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, sampling_locations: Tensor,
+                  attention_weights: Tensor, grad_output: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    B, S, M, D, L, Nq, P = _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    _require(grad_output.is_cuda, "grad_output must be a CUDA tensor")
+    grad_output = grad_output.to(value.dtype).contiguous()  # the reference asserts contiguity (cu:90); we normalise
+    _require(grad_output.shape == (B, Nq, M * D), "grad_output must be [B, Nq, M*D]")
+    code = _value_dtype_code(value)
+    grad_value = torch.empty_like(value)  # zeroed inside the library
+    grad_loc = torch.empty_like(sampling_locations)
+    grad_attn = torch.empty_like(attention_weights)
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_msda_backward_workspace_bytes(B, S, M, D, L, Nq, P, code)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        rc = L_.rdetr_msda_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_locations),
+                                    _ptr(attention_weights), _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc),
+                                    _ptr(grad_attn), B, S, M, D, L, Nq, P, code, _ptr(ws), ws_bytes, _stream(value))
+    _lib.check(rc, "rdetr_msda_backward")
+    return grad_value, grad_loc, grad_attn
+
+
+@msda_backward.register_fake
+def _(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output):
+    return torch.empty_like(value), torch.empty_like(sampling_locations), torch.empty_like(attention_weights)
+
+
+def _msda_setup_context(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _msda_autograd_backward(ctx, grad_output):
+    value, spatial_shapes, level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+    gv, gl, ga = msda_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_output)
+    return gv, None, None, gl, ga
+
+
+msda_forward.register_autograd(_msda_autograd_backward, setup_context=_msda_setup_context)
+
+
+def ms_deform_attn(value, value_spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    """Functional form; differentiable w.r.t. value, sampling_locations, attention_weights
+    (once-differentiable, like the reference: ms_deform_attn.py:64-65)."""
+    return msda_forward(value, value_spatial_shapes, level_start_index, sampling_locations, attention_weights)
+
+
+class MultiScaleDeformableAttnFunction:
+    """Call-compatible stand-in for the reference autograd.Function (ms_deform_attn.py:35-84):
+    ``MultiScaleDeformableAttnFunction.apply(value, shapes, level_start, loc, attn, im2col_step)``."""
+
+    @staticmethod
+    def apply(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, im2col_step=64):
+        batch = value.shape[0]
+        step = min(batch, int(im2col_step))
+        # the reference rejects batches that are not a multiple of the step (ms_deform_attn_cuda.cu:44)
+        _require(batch == 0 or (step > 0 and batch % step == 0), f"batch({batch}) must divide im2col_step({step})")
+        return msda_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+
+
+# ---- REL ----------------------------------------------------------------------------------------
+
+def relation_dim_t(num_pos_feats: int = 16, temperature: float = 10000.0, device=None) -> Tensor:
+    """``temperature ** (2k / num_pos_feats)`` in fp32, computed by torch exactly as the reference
+    does (position_encoding.py:101-105) so the kernel divides by bit-identical constants."""
+    dim_t = torch.arange(num_pos_feats // 2, dtype=torch.float32, device=device)
+    return temperature ** (dim_t * 2 / num_pos_feats)
+
+
+def _check_rel(src_boxes, tgt_boxes, weight, bias, dim_t):
+    for name, t in (("src_boxes", src_boxes), ("tgt_boxes", tgt_boxes), ("weight", weight), ("bias", bias), ("dim_t", dim_t)):
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.dtype == torch.float32, f"{name} must be float32")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    _require(src_boxes.dim() == 3 and src_boxes.shape[-1] == 4, "src_boxes much have 4 coordinates")
+    _require(tgt_boxes.dim() == 3 and tgt_boxes.shape[-1] == 4, "tgt_boxes must have 4 coordinates")
+    _require(src_boxes.shape[0] == tgt_boxes.shape[0], "src_boxes / tgt_boxes batch mismatch")
+    H = bias.shape[0]
+    _require(weight.numel() == H * 64 and dim_t.numel() == 8, "weight must hold [H, 64] values and dim_t 8")
+    return src_boxes.shape[0], src_boxes.shape[1], tgt_boxes.shape[1], H
+
+
+@torch.library.custom_op("rdetr::relation_forward", mutates_args=(), device_types="cuda")
+def relation_forward(src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias: Tensor, dim_t: Tensor, scale: float,
+                     eps: float, attn_mask: Optional[Tensor], fast: bool) -> Tuple[Tensor, Tensor]:
+    B, N1, N2, H = _check_rel(src_boxes, tgt_boxes, weight, bias, dim_t)
+    if attn_mask is not None:
+        _require(attn_mask.is_cuda and attn_mask.dtype == torch.bool and attn_mask.is_contiguous()
+                 and attn_mask.shape == (N1, N2), "attn_mask must be a contiguous CUDA bool tensor of shape [N1, N2]")
+    out = torch.empty((B, H, N1, N2), dtype=torch.float32, device=src_boxes.device)
+    bits = torch.empty((B, H, N1, (N2 + 31) // 32), dtype=torch.int32, device=src_boxes.device)
+    with torch.cuda.device(src_boxes.device):
+        rc = _lib.lib().rdetr_relation_forward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(weight), _ptr(bias), _ptr(dim_t),
+                                               float(scale), float(eps), _ptr(attn_mask), _ptr(out), _ptr(bits),
+                                               B, N1, N2, H, _lib.REL_FAST if fast else _lib.REL_EXACT, _stream(src_boxes))
+    _lib.check(rc, "rdetr_relation_forward")
+    return out, bits
+
+
+@relation_forward.register_fake
+def _(src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, fast):
+    B, N1, N2, H = src_boxes.shape[0], src_boxes.shape[1], tgt_boxes.shape[1], bias.shape[0]
+    return (src_boxes.new_empty((B, H, N1, N2)),
+            torch.empty((B, H, N1, (N2 + 31) // 32), dtype=torch.int32, device=src_boxes.device))
+
+
+@torch.library.custom_op("rdetr::relation_backward", mutates_args=(), device_types="cuda")
+def relation_backward(src_boxes: Tensor, tgt_boxes: Tensor, dim_t: Tensor, scale: float, eps: float, grad_out: Tensor,
+                      relu_bits: Tensor, num_heads: int, fast: bool) -> Tuple[Tensor, Tensor]:
+    B, N1, N2 = src_boxes.shape[0], src_boxes.shape[1], tgt_boxes.shape[1]
+    grad_out = grad_out.to(torch.float32).contiguous()
+    _require(grad_out.shape == (B, num_heads, N1, N2), "grad_out must be [B, H, N1, N2]")
+    gw = torch.empty((num_heads, 64), dtype=torch.float32, device=src_boxes.device)  # zeroed inside the library
+    gb = torch.empty((num_heads,), dtype=torch.float32, device=src_boxes.device)
+    with torch.cuda.device(src_boxes.device):
+        rc = _lib.lib().rdetr_relation_backward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(dim_t), float(scale), float(eps),
+                                                _ptr(grad_out), _ptr(relu_bits), _ptr(gw), _ptr(gb), B, N1, N2, num_heads,
+                                                _lib.REL_FAST if fast else _lib.REL_EXACT, _stream(src_boxes))
+    _lib.check(rc, "rdetr_relation_backward")
+    return gw, gb
+
+
+@relation_backward.register_fake
+def _(src_boxes, tgt_boxes, dim_t, scale, eps, grad_out, relu_bits, num_heads, fast):
+    return src_boxes.new_empty((num_heads, 64)), src_boxes.new_empty((num_heads,))
+
+
+def _rel_setup_context(ctx, inputs, output):
+    src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, fast = inputs
+    _, bits = output
+    # the output itself is NOT saved: the decoder mutates it in place (relation_transformer.py:372-374),
+    # which would trip autograd's version check; the 1-bit ReLU mask is what the backward needs.
+    ctx.save_for_backward(src_boxes, tgt_boxes, dim_t, bits)
+    ctx.scale, ctx.eps, ctx.fast = scale, eps, fast
+    ctx.num_heads = bias.shape[0]
+    ctx.weight_shape = weight.shape
+
+
+def _rel_autograd_backward(ctx, grad_out, grad_bits):
+    src_boxes, tgt_boxes, dim_t, bits = ctx.saved_tensors
+    gw, gb = relation_backward(src_boxes, tgt_boxes, dim_t, ctx.scale, ctx.eps, grad_out, bits, ctx.num_heads, ctx.fast)
+    # no gradient reaches the boxes: the reference computes the geometry under no_grad (:527-529)
+    return None, None, gw.view(ctx.weight_shape), gb, None, None, None, None, None
+
+
+relation_forward.register_autograd(_rel_autograd_backward, setup_context=_rel_setup_context)
+
+
+def position_relation_bias(src_boxes: Tensor, tgt_boxes: Optional[Tensor], weight: Tensor, bias: Tensor,
+                           dim_t: Optional[Tensor] = None, scale: float = 100.0, eps: float = 1e-5,
+                           attn_mask: Optional[Tensor] = None, fast: bool = False) -> Tensor:
+    """boxes in -> ``[B, H, N1, N2]`` fp32 bias out (>= 0, or -inf where ``attn_mask``); differentiable
+    w.r.t. ``weight`` ([H,64] or [H,64,1,1]) and ``bias`` only."""
+    if tgt_boxes is None:
+        tgt_boxes = src_boxes
+    if dim_t is None:
+        dim_t = relation_dim_t(16, 10000.0, src_boxes.device)
+    out, _ = relation_forward(src_boxes.detach().float().contiguous(), tgt_boxes.detach().float().contiguous(),
+                              weight.float().contiguous(), bias.float().contiguous(), dim_t, scale, eps, attn_mask, fast)
+    return out

@@ -1,0 +1,48 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+MSDA_GOLDEN = ["msda_tiny_U", "msda_tiny_oob", "msda_tiny_strict", "msda_pyr4_S", "msda_pyr5_D", "msda_h4_p2"]
+REL_GOLDEN = ["rel_tiny", "rel_self", "rel_degenerate", "rel_cdn_mask", "rel_one"]
+
+
+def maxabs(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+def relmax(a, ref):
+    """max|a-ref| / max|ref| -- the gradient metric of SURVEY.md 8c."""
+    ref = np.asarray(ref, dtype=np.float64)
+    den = float(np.max(np.abs(ref))) if ref.size else 1.0
+    return maxabs(a, ref) / max(den, 1e-30)

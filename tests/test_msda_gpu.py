@@ -1,0 +1,241 @@
+"""MSDA parity on the B200: the CUDA path (through the C ABI) vs the oracle.
+
+Tolerances (fp32): forward max-abs <= 1e-5 vs the fp64 reference on the committed fixtures
+(north star); gradients max-abs-error / max-abs-reference <= 1e-4; grad_sampling_loc is checked
+strictly only for locations kept away from pixel boundaries (bilinear d/dloc is discontinuous
+there) and otherwise by the fraction of elements off by more than the tolerance.
+bf16 value path: forward <= 1e-2, gradients <= 2e-2 (relative to max-abs of the reference).
+"""
+import numpy as np
+import pytest
+import torch
+
+import relation_detr_b200 as rd
+from relation_detr_b200 import ops, workloads
+from conftest import MSDA_GOLDEN, load_golden, maxabs, relmax
+from oracle import c_oracle, torch_port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_ours(inp, dtype=torch.float32):
+    v = inp["value"].to(DEV, dtype).requires_grad_(True)
+    loc = inp["sampling_locations"].to(DEV, torch.float32).requires_grad_(True)
+    attn = inp["attention_weights"].to(DEV, torch.float32).requires_grad_(True)
+    out = ops.ms_deform_attn(v, inp["spatial_shapes"].to(DEV), inp["level_start_index"].to(DEV), loc, attn)
+    out.backward(inp["grad_output"].to(DEV, dtype))
+    torch.cuda.synchronize()
+    return dict(out=out.detach().float().cpu().numpy(), grad_value=v.grad.float().cpu().numpy(),
+                grad_loc=loc.grad.cpu().numpy(), grad_attn=attn.grad.cpu().numpy())
+
+
+def run_torch_oracle(inp, dtype=torch.float64, device=DEV):
+    v = inp["value"].to(device, dtype).requires_grad_(True)
+    loc = inp["sampling_locations"].to(device, dtype).requires_grad_(True)
+    attn = inp["attention_weights"].to(device, dtype).requires_grad_(True)
+    out = torch_port.msda_grid_sample(v, inp["spatial_shapes"].to(device), loc, attn)
+    out.backward(inp["grad_output"].to(device, dtype))
+    return dict(out=out.detach().cpu().numpy(), grad_value=v.grad.cpu().numpy(),
+                grad_loc=loc.grad.cpu().numpy(), grad_attn=attn.grad.cpu().numpy())
+
+
+def golden_inputs(g):
+    return {k: torch.from_numpy(g[k]) for k in ("value", "spatial_shapes", "level_start_index",
+                                                 "sampling_locations", "attention_weights", "grad_output")}
+
+
+@pytest.mark.parametrize("name", MSDA_GOLDEN)
+def test_fp32_matches_reference_fixtures(name):
+    g = load_golden(name)
+    r = run_ours(golden_inputs(g))
+    assert maxabs(r["out"], g["ref64_out"]) <= 1e-5
+    assert relmax(r["grad_value"], g["ref64_grad_value"]) <= 1e-4
+    assert relmax(r["grad_attn"], g["ref64_grad_attn"]) <= 1e-4
+    if "strict" in name:
+        assert relmax(r["grad_loc"], g["ref64_grad_loc"]) <= 1e-4
+    else:
+        ref = g["ref64_grad_loc"]
+        bad = np.abs(r["grad_loc"] - ref) > 1e-4 * np.abs(ref).max()
+        assert bad.mean() <= 2e-3, f"{bad.mean():.2e} of grad_loc elements off (floor() flips expected ~1e-5)"
+
+
+@pytest.mark.parametrize("name", ["msda_tiny_U", "msda_pyr4_S", "msda_pyr5_D"])
+def test_bf16_value_path_matches_reference_fixtures(name):
+    g = load_golden(name)
+    inp = golden_inputs(g)
+    # the oracle sees the same bf16-rounded value / grad_out, in fp64
+    inp["value"] = inp["value"].bfloat16().float()
+    inp["grad_output"] = inp["grad_output"].bfloat16().float()
+    ref = run_torch_oracle(inp, torch.float64, "cpu")
+    r = run_ours(inp, torch.bfloat16)
+    assert relmax(r["out"], ref["out"]) <= 1e-2
+    assert relmax(r["grad_value"], ref["grad_value"]) <= 2e-2
+    assert relmax(r["grad_attn"], ref["grad_attn"]) <= 1e-4  # fp32 outputs: only the inputs were rounded
+    assert np.isfinite(r["grad_loc"]).all()
+
+
+@pytest.mark.parametrize("loc_kind", ["U", "S", "D", "oob", "strict"])
+def test_fp32_matches_c_oracle_on_seeded_inputs(loc_kind):
+    shape = workloads.MsdaShape("t", 2, ((25, 42), (13, 21), (7, 11), (4, 6)), 300)
+    inp = workloads.make_msda_inputs(shape, loc_kind, seed=11)
+    a = {k: v.numpy() for k, v in inp.items()}
+    args64 = [a["value"].astype(np.float64), a["spatial_shapes"], a["level_start_index"],
+              a["sampling_locations"].astype(np.float64), a["attention_weights"].astype(np.float64)]
+    o64 = c_oracle.msda_forward(*args64)
+    gv64, gl64, ga64 = c_oracle.msda_backward(*args64, a["grad_output"].astype(np.float64))
+    r = run_ours(inp)
+    assert maxabs(r["out"], o64) <= 1e-5
+    assert relmax(r["grad_value"], gv64) <= 1e-4
+    assert relmax(r["grad_attn"], ga64) <= 1e-4
+    if loc_kind == "strict":
+        assert relmax(r["grad_loc"], gl64) <= 1e-4
+    else:
+        bad = np.abs(r["grad_loc"] - gl64) > 1e-4 * np.abs(gl64).max()
+        assert bad.mean() <= 1e-3
+
+
+@pytest.mark.parametrize("L,P,M", [(1, 1, 8), (5, 4, 8), (4, 8, 8), (8, 2, 4), (2, 3, 5)])
+def test_level_point_head_counts(L, P, M):
+    levels = tuple((max(2, 20 >> i), max(3, 28 >> i)) for i in range(L))
+    shape = workloads.MsdaShape("t", 2, levels, 53, heads=M, points=P)
+    inp = workloads.make_msda_inputs(shape, "oob", seed=L * 10 + P)
+    ref = run_torch_oracle(inp, torch.float64)
+    r = run_ours(inp)
+    assert maxabs(r["out"], ref["out"]) <= 1e-5
+    assert relmax(r["grad_value"], ref["grad_value"]) <= 1e-4
+    assert relmax(r["grad_attn"], ref["grad_attn"]) <= 1e-4
+
+
+def test_ragged_tail_and_empty_inputs():
+    # Nq*M not a multiple of the pairs-per-CTA tile; Nq = 0; B = 0
+    ss, lsi = workloads.shape_tensors(((5, 7), (3, 4)), DEV)
+    S = 35 + 12
+    for B, Nq in ((1, 1), (1, 33), (3, 5), (2, 0), (0, 4)):
+        g = torch.Generator(device=DEV).manual_seed(B * 100 + Nq)
+        v = torch.randn((B, S, 8, 32), device=DEV, generator=g)
+        loc = torch.rand((B, Nq, 8, 2, 4, 2), device=DEV, generator=g)
+        attn = torch.rand((B, Nq, 8, 2, 4), device=DEV, generator=g)
+        out = ops.ms_deform_attn(v, ss, lsi, loc, attn)
+        assert out.shape == (B, Nq, 256)
+        if B and Nq:
+            ref = torch_port.msda_grid_sample(v.double(), ss, loc.double(), attn.double())
+            assert (out.double() - ref).abs().max().item() <= 1e-5
+        gv, gl, ga = ops.msda_backward(v, ss, lsi, loc, attn, torch.ones_like(out))
+        assert gv.shape == v.shape and gl.shape == loc.shape and ga.shape == attn.shape
+        if B and Nq == 0:
+            assert torch.count_nonzero(gv) == 0
+
+
+def test_outside_and_nan_locations_contribute_nothing():
+    ss, lsi = workloads.shape_tensors(((4, 6),), DEV)
+    v = torch.randn((1, 24, 8, 32), device=DEV)
+    v[0, 0] = float("inf")  # a poisoned pixel must not leak through zero-weight / invalid corners
+    loc = torch.tensor([[-3.0, 0.5], [0.5, 7.0], [float("nan"), 0.5], [-1.0 / 12, 0.5]], device=DEV)  # last: w_im == -1
+    loc = loc.view(1, 1, 1, 1, 4, 2).expand(1, 2, 8, 1, 4, 2).contiguous()
+    attn = torch.full((1, 2, 8, 1, 4), 0.25, device=DEV)
+    out = ops.ms_deform_attn(v, ss, lsi, loc, attn)
+    assert torch.count_nonzero(out) == 0
+    gv, gl, ga = ops.msda_backward(v, ss, lsi, loc, attn, torch.ones_like(out))
+    assert torch.count_nonzero(gv) == 0 and torch.count_nonzero(gl) == 0 and torch.count_nonzero(ga) == 0
+
+
+def test_reference_preconditions_raise():
+    inp = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "U")
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ops.ms_deform_attn(d["value"].transpose(1, 2).contiguous().transpose(1, 2), d["spatial_shapes"],
+                           d["level_start_index"], d["sampling_locations"], d["attention_weights"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.ms_deform_attn(d["value"], d["spatial_shapes"].cpu(), d["level_start_index"], d["sampling_locations"],
+                           d["attention_weights"])
+    with pytest.raises(RuntimeError, match="D=16"):
+        ops.ms_deform_attn(d["value"].view(2, -1, 16, 16).contiguous(), d["spatial_shapes"], d["level_start_index"],
+                           torch.rand(2, 5, 16, 3, 4, 2, device=DEV), torch.rand(2, 5, 16, 3, 4, device=DEV))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_encoder_properties(dtype):
+    """BASELINE configs[1] shape (B=8, S=Nq=22323): size-independent properties instead of the oracle.
+    (1) linearity in value and in attention; (2) the adjoint identity <G, F(V)> = <F^T(G), V> that
+    ties backward to forward; (3) a batch-slice equals the same call on that slice alone."""
+    shape = workloads.MSDA_SHAPES["msda_enc_800x1333_b8"]
+    inp = workloads.make_msda_inputs(shape, "S", seed=0, device=DEV)
+    v, ss, lsi = inp["value"].to(dtype), inp["spatial_shapes"], inp["level_start_index"]
+    loc, attn, go = inp["sampling_locations"], inp["attention_weights"], inp["grad_output"].to(dtype)
+    out = ops.ms_deform_attn(v, ss, lsi, loc, attn)
+    assert out.shape == (8, 22323, 256) and torch.isfinite(out).all()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    # (3) batch independence
+    out3 = ops.ms_deform_attn(v[3:4].contiguous(), ss, lsi, loc[3:4].contiguous(), attn[3:4].contiguous())
+    assert torch.equal(out3, out[3:4])
+    # (1) linearity: F(2V) = 2F(V) exactly (power-of-two scaling), F(attn/2) = F(attn)/2
+    assert torch.equal(ops.ms_deform_attn(v * 2, ss, lsi, loc, attn), out * 2)
+    assert (ops.ms_deform_attn(v, ss, lsi, loc, attn * 0.5).float() - out.float() * 0.5).abs().max() <= tol
+    # (2) adjoint identity, accumulated in fp64
+    gv, gl, ga = ops.msda_backward(v, ss, lsi, loc, attn, go)
+    lhs = (go.double() * out.double()).sum().item()
+    rhs = (gv.double() * v.double()).sum().item()
+    rhs_attn = (ga.double() * attn.double()).sum().item()  # F is also linear in attn
+    scale = (go.double().abs() * out.double().abs()).sum().item()
+    rel = 1e-6 if dtype == torch.float32 else 5e-3
+    assert abs(lhs - rhs) <= rel * scale, (lhs, rhs, scale)
+    assert abs(lhs - rhs_attn) <= rel * scale, (lhs, rhs_attn, scale)
+    assert torch.isfinite(gl).all()
+
+
+def test_full_size_against_gpu_oracle_one_image():
+    """800x1333 pyramid, B=1: the grid_sample oracle on the same device (fp64 and fp32), with the
+    oracle's own fp32 noise reported next to ours."""
+    shape = workloads.MSDA_SHAPES["msda_enc_800x1333_b1"]
+    inp = workloads.make_msda_inputs(shape, "U", seed=5, device=DEV)
+    ref64 = run_torch_oracle(inp, torch.float64)
+    ref32 = run_torch_oracle(inp, torch.float32)
+    r = run_ours(inp)
+    ours = maxabs(r["out"], ref64["out"])
+    floor = maxabs(ref32["out"], ref64["out"])
+    print(f"\nfull-size fwd max-abs: ours {ours:.2e}  oracle-fp32 noise {floor:.2e}")
+    assert ours <= max(1e-5, 1.5 * floor)
+    assert relmax(r["grad_value"], ref64["grad_value"]) <= 1e-4
+    assert relmax(r["grad_attn"], ref64["grad_attn"]) <= 1e-4
+    bad = np.abs(r["grad_loc"] - ref64["grad_loc"]) > 1e-4 * np.abs(ref64["grad_loc"]).max()
+    print(f"grad_loc elements over tolerance: {bad.mean():.2e}")
+    assert bad.mean() <= 1e-3
+
+
+def test_module_matches_torch_port_pipeline():
+    """Drop-in module (2-d and 4-d reference points, padding mask) vs the same module math with the
+    oracle in place of the kernel."""
+    torch.manual_seed(0)
+    mod = rd.MultiScaleDeformableAttention(256, 4, 8, 4).to(DEV)
+    with torch.no_grad():  # non-trivial offsets / weights
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    levels = ((13, 21), (7, 11), (4, 6), (2, 3))
+    ss, lsi = workloads.shape_tensors(levels, DEV)
+    S = int(ss.prod(1).sum())
+    B, Nq = 2, 40
+    g = torch.Generator(device=DEV).manual_seed(1)
+    query = torch.randn((B, Nq, 256), device=DEV, generator=g)
+    value = torch.randn((B, S, 256), device=DEV, generator=g)
+    mask = torch.rand((B, S), device=DEV, generator=g) > 0.9
+    for ref_dim in (2, 4):
+        refp = torch.rand((B, Nq, 4, ref_dim), device=DEV, generator=g) * 0.8 + 0.1
+        out = mod(query, refp, value, ss, lsi, mask)
+        # oracle pipeline
+        with torch.no_grad():
+            v = mod.value_proj(value).masked_fill(mask[..., None], 0.0).view(B, S, 8, 32)
+            off = mod.sampling_offsets(query).view(B, Nq, 8, 4, 4, 2)
+            w = mod.attention_weights(query).view(B, Nq, 8, 16).softmax(-1).view(B, Nq, 8, 4, 4)
+            if ref_dim == 2:
+                wh = torch.stack([ss[..., 1], ss[..., 0]], -1)
+                loc = refp[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+            else:
+                loc = refp[:, :, None, :, None, :2] + off / 4 * refp[:, :, None, :, None, 2:] * 0.5
+            want = mod.output_proj(torch_port.msda_grid_sample(v, ss, loc, w))
+        assert (out - want).abs().max().item() <= 2e-5
+    out.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ob = mod(query, refp, value, ss, lsi, mask)
+    assert ob.dtype == torch.bfloat16 and (ob.float() - out).abs().max().item() <= 0.1
