@@ -72,12 +72,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
-// Per-lane slice of one (pixel, head) row of `value`: 16 bytes = 4 fp32 or 8 bf16 channels.
-template <typename VT>
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+// Per-lane slice of one (pixel, head) row of `value`: CH channels held by one lane.
+//   <float, 4>  16-byte loads, 8 lanes per D=32 row (one 128-byte line per row)
+//   <bf16, 8>   16-byte loads, 4 lanes per row (64 bytes per row)
+//   <bf16, 4>    8-byte loads, 8 lanes per row; used where each lane must still issue full
+//                16-byte fp32 vector reductions (backward)
+template <typename VT, int CH>
 struct Slice;
 
 template <>
-struct Slice<float> {
+struct Slice<float, 4> {
     static constexpr int kCh = 4;
     __device__ __forceinline__ static void load(const float *p, float (&v)[4])
     {
@@ -96,7 +107,7 @@ struct Slice<float> {
 };
 
 template <>
-struct Slice<__nv_bfloat16> {
+struct Slice<__nv_bfloat16, 8> {
     static constexpr int kCh = 8;
     __device__ __forceinline__ static void unpack(const uint4 t, float (&v)[8])
     {
@@ -117,6 +128,29 @@ struct Slice<__nv_bfloat16> {
         t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
         t.z = pack_bf16(v[4], v[5]); t.w = pack_bf16(v[6], v[7]);
         *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+
+template <>
+struct Slice<__nv_bfloat16, 4> {
+    static constexpr int kCh = 4;
+    __device__ __forceinline__ static void unpack(const uint2 t, float (&v)[4])
+    {
+        v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
+    }
+    __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&v)[4])
+    {
+        unpack(__ldg(reinterpret_cast<const uint2 *>(p)), v);
+    }
+    __device__ __forceinline__ static void load_stream(const __nv_bfloat16 *p, float (&v)[4])
+    {
+        unpack(ld_stream_u2(reinterpret_cast<const uint2 *>(p)), v);
+    }
+    __device__ __forceinline__ static void store(__nv_bfloat16 *p, const float (&v)[4])
+    {
+        uint2 t;
+        t.x = pack_bf16(v[0], v[1]); t.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = t;
     }
 };
 

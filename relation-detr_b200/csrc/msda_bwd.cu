@@ -7,7 +7,9 @@
 // Same work layout as the forward (see msda_fwd.cu):
 //   * phase 1, one thread per sample: corner pixel indices, fractional offsets and the attention
 //     weight staged in shared memory (32 B per sample);
-//   * phase 2, 16 B of channels per lane, kLanes lanes per (b,q,m): re-gather the four corners,
+//   * phase 2, 4 channels per lane, 8 lanes per (b,q,m) for fp32 AND bf16 (so that every lane's
+//     reduction is a full 16-byte fp32 vector and every corner one 128-byte request: the L2 atomic
+//     unit is request-rate bound, measured in profiles/): re-gather the four corners,
 //       - grad_value: one vector reduction (red.global.add.v4.f32, 16 B per lane => a whole
 //         128-byte row per corner for fp32) instead of 32 scalar atomics;
 //       - grad_attn / grad_loc: per-lane partial dot products over its channels, combined with
@@ -26,7 +28,7 @@ int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, in
 
 constexpr int kBwdThreads = 256;
 
-template <typename VT, int D>
+template <typename VT, int CH, int D>
 __global__ void __launch_bounds__(kBwdThreads)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
@@ -34,7 +36,8 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, int L, int Nq, int P,
                 long long total_pairs)
 {
-    constexpr int kCh = Slice<VT>::kCh;
+    using SL = Slice<VT, CH>;
+    constexpr int kCh = CH;
     constexpr int kLanes = D / kCh;
     constexpr int kPairs = kBwdThreads / kLanes;
 
@@ -88,7 +91,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     float g[kCh];
 #pragma unroll
     for (int c = 0; c < kCh; ++c) g[c] = 0.f;
-    if (active) Slice<VT>::load_stream(grad_out + gp * D + lane * kCh, g);
+    if (active) SL::load_stream(grad_out + gp * D + lane * kCh, g);
 
     const int4 *my_pix = s_pix + pair * stride;
     float4 *my_meta = s_meta + pair * stride;
@@ -105,10 +108,10 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
 #pragma unroll
         for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
-        if (px.x >= 0) Slice<VT>::load(vbase + (long long)px.x * pix_stride, v0);
-        if (px.y >= 0) Slice<VT>::load(vbase + (long long)px.y * pix_stride, v1);
-        if (px.z >= 0) Slice<VT>::load(vbase + (long long)px.z * pix_stride, v2);
-        if (px.w >= 0) Slice<VT>::load(vbase + (long long)px.w * pix_stride, v3);
+        if (px.x >= 0) SL::load(vbase + (long long)px.x * pix_stride, v0);
+        if (px.y >= 0) SL::load(vbase + (long long)px.y * pix_stride, v1);
+        if (px.z >= 0) SL::load(vbase + (long long)px.z * pix_stride, v2);
+        if (px.w >= 0) SL::load(vbase + (long long)px.w * pix_stride, v3);
 
         const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
         float p_attn = 0.f, p_gw = 0.f, p_gh = 0.f;
@@ -170,17 +173,17 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
     reinterpret_cast<uint4 *>(dst)[i] = t;
 }
 
-template <typename VT>
+template <typename VT, int CH>
 static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
                       const void *grad_out, float *gv_f32, float *grad_loc, float *grad_attn, int B, int S, int M, int L,
                       int Nq, int P, cudaStream_t stream)
 {
     constexpr int D = 32;
-    constexpr int kLanes = D / Slice<VT>::kCh;
+    constexpr int kLanes = D / CH;
     constexpr int kPairs = kBwdThreads / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
-    auto kern = msda_bwd_kernel<VT, D>;
+    auto kern = msda_bwd_kernel<VT, CH, D>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_bwd)"))
@@ -231,10 +234,10 @@ extern "C" int rdetr_msda_backward(const void *value, const int64_t *spatial_sha
     if (Nq > 0) {
         int rc;
         if (value_dtype == RDETR_DTYPE_F32)
-            rc = launch_bwd<float>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+            rc = launch_bwd<float, 4>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
                                    grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
         else
-            rc = launch_bwd<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_locations,
+            rc = launch_bwd<__nv_bfloat16, 4>(value, spatial_shapes, level_start_index, sampling_locations,
                                            attention_weights, grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
         if (rc) return rc;
     }

@@ -22,14 +22,15 @@ namespace rdetr {
 
 constexpr int kFwdThreads = 256;
 
-template <typename VT, int D>
+template <typename VT, int CH, int D>
 __global__ void __launch_bounds__(kFwdThreads)
 msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
                 const float *__restrict__ attn, VT *__restrict__ out, int S, int M, int L, int Nq,
                 int P, long long total_pairs)
 {
-    constexpr int kCh = Slice<VT>::kCh;
+    using SL = Slice<VT, CH>;
+    constexpr int kCh = CH;
     constexpr int kLanes = D / kCh;
     constexpr int kPairs = kFwdThreads / kLanes;
 
@@ -92,10 +93,10 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
 #pragma unroll
         for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
-        if (px.x >= 0) Slice<VT>::load(vbase + (long long)px.x * pix_stride, v0);
-        if (px.y >= 0) Slice<VT>::load(vbase + (long long)px.y * pix_stride, v1);
-        if (px.z >= 0) Slice<VT>::load(vbase + (long long)px.z * pix_stride, v2);
-        if (px.w >= 0) Slice<VT>::load(vbase + (long long)px.w * pix_stride, v3);
+        if (px.x >= 0) SL::load(vbase + (long long)px.x * pix_stride, v0);
+        if (px.y >= 0) SL::load(vbase + (long long)px.y * pix_stride, v1);
+        if (px.z >= 0) SL::load(vbase + (long long)px.z * pix_stride, v2);
+        if (px.w >= 0) SL::load(vbase + (long long)px.w * pix_stride, v3);
 #pragma unroll
         for (int c = 0; c < kCh; ++c) {
             acc[c] = fmaf(w.x, v0[c], acc[c]);
@@ -104,20 +105,20 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
             acc[c] = fmaf(w.w, v3[c], acc[c]);
         }
     }
-    Slice<VT>::store(out + gp * D + lane * kCh, acc);
+    SL::store(out + gp * D + lane * kCh, acc);
 }
 
-template <typename VT>
+template <typename VT, int CH>
 static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
                       const float *attn, void *out, int B, int S, int M, int L, int Nq, int P,
                       cudaStream_t stream)
 {
     constexpr int D = 32;
-    constexpr int kLanes = D / Slice<VT>::kCh;
+    constexpr int kLanes = D / CH;
     constexpr int kPairs = kFwdThreads / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
-    auto kern = msda_fwd_kernel<VT, D>;
+    auto kern = msda_fwd_kernel<VT, CH, D>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_fwd)"))
@@ -162,8 +163,8 @@ extern "C" int rdetr_msda_forward(const void *value, const int64_t *spatial_shap
     if (int rc = enter_device_of(value)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (value_dtype == RDETR_DTYPE_F32)
-        return launch_fwd<float>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, out, B,
+        return launch_fwd<float, 4>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, out, B,
                                  S, M, L, Nq, P, st);
-    return launch_fwd<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+    return launch_fwd<__nv_bfloat16, 8>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
                                      out, B, S, M, L, Nq, P, st);
 }

@@ -20,9 +20,9 @@ DEV = "cuda:0"
 
 
 def run_ours(inp, dtype=torch.float32):
-    v = inp["value"].to(DEV, dtype).requires_grad_(True)
-    loc = inp["sampling_locations"].to(DEV, torch.float32).requires_grad_(True)
-    attn = inp["attention_weights"].to(DEV, torch.float32).requires_grad_(True)
+    v = inp["value"].detach().to(DEV, dtype).clone().requires_grad_(True)
+    loc = inp["sampling_locations"].detach().to(DEV, torch.float32).clone().requires_grad_(True)
+    attn = inp["attention_weights"].detach().to(DEV, torch.float32).clone().requires_grad_(True)
     out = ops.ms_deform_attn(v, inp["spatial_shapes"].to(DEV), inp["level_start_index"].to(DEV), loc, attn)
     out.backward(inp["grad_output"].to(DEV, dtype))
     torch.cuda.synchronize()
@@ -31,9 +31,9 @@ def run_ours(inp, dtype=torch.float32):
 
 
 def run_torch_oracle(inp, dtype=torch.float64, device=DEV):
-    v = inp["value"].to(device, dtype).requires_grad_(True)
-    loc = inp["sampling_locations"].to(device, dtype).requires_grad_(True)
-    attn = inp["attention_weights"].to(device, dtype).requires_grad_(True)
+    v = inp["value"].detach().to(device, dtype).clone().requires_grad_(True)
+    loc = inp["sampling_locations"].detach().to(device, dtype).clone().requires_grad_(True)
+    attn = inp["attention_weights"].detach().to(device, dtype).clone().requires_grad_(True)
     out = torch_port.msda_grid_sample(v, inp["spatial_shapes"].to(device), loc, attn)
     out.backward(inp["grad_output"].to(device, dtype))
     return dict(out=out.detach().cpu().numpy(), grad_value=v.grad.cpu().numpy(),

@@ -67,10 +67,15 @@ def test_matches_c_oracle_on_seeded_inputs(B, N1, N2):
         out, gw, gb = run_ours(src, tgt, w, b, r["grad_output"], None, fast)
         assert maxabs(out, o64) <= (1e-4 if fast else 5e-5), fast
         assert np.abs(out - o64).mean() <= (5e-6 if fast else 2e-6), fast
-        # sign disagreements of the pre-activation can only happen within rounding of zero
+        # sign disagreements of the pre-activation can only happen within rounding of zero ...
         flips = (out > 0) != (o64 > 0)
         assert np.abs(o64[flips]).max(initial=0.0) <= 1e-4
-        assert relmax(gw, gw64) <= 5e-4 and relmax(gb, gb64) <= 5e-4
+        # ... but each one moves grad_weight[h, :] by up to |grad_out| (|f| <= 1): ReLU'(0) is as
+        # discontinuous as floor() is for grad_loc, so the tolerance carries that per-head slack
+        slack = (np.abs(r["grad_output"].numpy()) * flips).sum(axis=(0, 2, 3))
+        tol = 5e-4 * np.abs(gw64).max()
+        assert (np.abs(gw - gw64).max(axis=1) <= tol + slack).all(), (np.abs(gw - gw64).max(axis=1), slack)
+        assert (np.abs(gb - gb64) <= 5e-4 * np.abs(gb64).max() + slack).all()
 
 
 def test_exact_mode_features_match_torch_on_the_same_device():
