@@ -104,14 +104,19 @@ int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes,
  *   attn_mask  NULL or [N1, N2] bytes (torch.bool); non-zero => out = -inf (the decoder's
  *              masked_fill_, relation_transformer.py:372-374, fused)
  *   out        [B, H, N1, N2] fp32
- *   relu_bits  NULL or [B, H, N1, ceil(N2/32)] uint32; bit (j%32) of word j/32 = pre-activation > 0.
- *              Needed by the backward because the caller mutates `out` in place.
+ *   relu_bits  NULL or [B, N1, ceil(N2/32), H] uint32 (16-byte aligned); bit (j%32) of word
+ *              [b, i, j/32, h] = pre-activation of out[b,h,i,j] > 0.  Needed by the backward because
+ *              the caller mutates `out` in place.
+ *   workspace  rdetr_relation_workspace_bytes() bytes of device scratch (per-box sin/cos tables of
+ *              the FAST mode; 0 bytes / may be NULL in EXACT mode); contents undefined on return.
  * Supported: H == 8, 64 input features (num_pos_feats 16 x 4 box features).
  */
+size_t rdetr_relation_workspace_bytes(int B, int N1, int N2, int flags);
 int rdetr_relation_forward(const float *src_boxes, const float *tgt_boxes, const float *weight,
                            const float *bias, const float *dim_t, float scale, float eps,
                            const uint8_t *attn_mask, float *out, uint32_t *relu_bits, int B, int N1,
-                           int N2, int H, int flags, rdetr_stream_t stream);
+                           int N2, int H, int flags, void *workspace, size_t workspace_bytes,
+                           rdetr_stream_t stream);
 
 /*
  * Fused position-relation embedding, backward (parameters only; boxes carry no gradient because
@@ -121,11 +126,13 @@ int rdetr_relation_forward(const float *src_boxes, const float *tgt_boxes, const
  *   grad_out    [B, H, N1, N2] fp32
  *   relu_bits   as written by the forward (required)
  *   grad_weight [H, 64] fp32, grad_bias [H] fp32: ZEROED INSIDE this call, then accumulated
+ *   workspace   as for the forward (same size; the tables are recomputed)
  */
 int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, const float *dim_t,
                             float scale, float eps, const float *grad_out,
                             const uint32_t *relu_bits, float *grad_weight, float *grad_bias, int B,
-                            int N1, int N2, int H, int flags, rdetr_stream_t stream);
+                            int N1, int N2, int H, int flags, void *workspace,
+                            size_t workspace_bytes, rdetr_stream_t stream);
 
 #ifdef __cplusplus
 }

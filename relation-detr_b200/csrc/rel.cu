@@ -12,38 +12,61 @@
 //   e2 = log((w1+eps) / (w2+eps))      e3 = log((h1+eps) / (h2+eps))
 //   theta[c,k] = (e_c * scale) / dim_t[k];  f[c*16+2k] = sin(theta), f[c*16+2k+1] = cos(theta)
 //   out[h] = relu(bias[h] + sum_n W[h,n] f[n])
-// EXACT mode keeps (e*scale)/dim_t with an IEEE division and the accurate sinf/cosf so the features
-// are bit-identical to what torch computes on the same device; FAST mode replaces the division by a
-// reciprocal multiply with one FMA correction step and sin/cos by a two-term Cody-Waite reduction
-// followed by the MUFU approximations (abs error ~4e-7 per feature).
+//
+// EXACT mode keeps every operation of that chain as torch evaluates it on CUDA (IEEE divisions,
+// logf, (e*scale)/dim_t, sinf/cosf), so the 64 features are bit-identical to the eager path on the
+// same device and only the order of the 64-term sum differs.
+//
+// FAST mode restructures the arithmetic (the op is FP32-pipe bound, not HBM bound: 512 FMA + 64
+// transcendentals per pair for 32 bytes of output):
+//   * the two size features are separable, e2 = log(w1+eps) - log(w2+eps), so sin/cos(theta) for
+//     c = 2,3 come from per-box tables sin/cos(A_i), sin/cos(B_j) (computed once per box in fp64 by
+//     a tiny pre-kernel) through the angle-difference identities: 4 FMA-pipe ops per angle and no
+//     per-pair transcendental for half of the features;
+//   * for the two centre features the per-row reciprocal 1/(w1+eps) replaces the division, the
+//     division by dim_t becomes a multiply with one FMA correction step, and sin/cos use a
+//     two-term Cody-Waite reduction followed by MUFU.SIN / MUFU.COS.
+// Both modes walk kRowsPerIter src rows per thread so that each shared-memory weight fetch feeds
+// kRowsPerIter * 4 FMAs.
 #include "common.cuh"
 
 namespace rdetr {
 
 constexpr int kRelHeads = 8;
-constexpr int kRelK = 8;          // frequencies per box feature
+constexpr int kRelK = 8;             // frequencies per box feature
 constexpr int kRelFeat = 8 * kRelK;  // 4 features x K x (sin, cos) = 64
+constexpr int kTab = 36;             // floats per box in the FAST tables (144 B, 16-byte aligned)
+// table row: [0]=cx [1]=cy [2]=1/(w+eps) [3]=1/(h+eps) [4..11]=sin(Aw_k) [12..19]=sin(Ah_k)
+//            [20..27]=cos(Aw_k) [28..35]=cos(Ah_k),  A*_k = log(size+eps) * scale / dim_t[k]
 
-__device__ __forceinline__ void pair_features(const float4 s, const float4 t, float eps, float (&e)[4])
+__global__ void __launch_bounds__(128)
+rel_tables_kernel(const float *__restrict__ boxes, const float *__restrict__ dim_t, float scale, float eps,
+                  float *__restrict__ table, int nboxes)
 {
-    // true divisions, as torch evaluates them (relation_transformer.py:485-488)
-    e[0] = logf(fabsf(s.x - t.x) / (s.z + eps) + 1.0f);
-    e[1] = logf(fabsf(s.y - t.y) / (s.w + eps) + 1.0f);
-    e[2] = logf((s.z + eps) / (t.z + eps));
-    e[3] = logf((s.w + eps) / (t.w + eps));
-}
-
-// only feature c of the four (c is warp-uniform in the backward)
-__device__ __forceinline__ float pair_feature(int c, const float4 s, const float4 t, float eps)
-{
-    switch (c) {
-        case 0: return logf(fabsf(s.x - t.x) / (s.z + eps) + 1.0f);
-        case 1: return logf(fabsf(s.y - t.y) / (s.w + eps) + 1.0f);
-        case 2: return logf((s.z + eps) / (t.z + eps));
-        default: return logf((s.w + eps) / (t.w + eps));
+    // one thread per (box, k): 16 double-precision sin/cos pairs per box, nboxes ~ 1e4 => negligible
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int box = idx >> 3, k = idx & 7;
+    if (box >= nboxes) return;
+    const float4 bx = __ldg(reinterpret_cast<const float4 *>(boxes) + box);
+    const float we = bx.z + eps, he = bx.w + eps;  // rounded to fp32 exactly as the reference does
+    float *row = table + (size_t)box * kTab;
+    if (k == 0) {
+        row[0] = bx.x;
+        row[1] = bx.y;
+        row[2] = 1.0f / we;
+        row[3] = 1.0f / he;
     }
+    const double f = (double)scale / (double)__ldg(dim_t + k);
+    double s, c;
+    sincos(log((double)we) * f, &s, &c);
+    row[4 + k] = (float)s;
+    row[20 + k] = (float)c;
+    sincos(log((double)he) * f, &s, &c);
+    row[12 + k] = (float)s;
+    row[28 + k] = (float)c;
 }
 
+// sin/cos of q = es / d for the centre features
 template <bool FAST>
 __device__ __forceinline__ void angle_sincos(float es, float d, float inv_d, float &sn, float &cs)
 {
@@ -66,111 +89,256 @@ __device__ __forceinline__ void angle_sincos(float es, float d, float inv_d, flo
     }
 }
 
+// Packed fp32 pairs (Blackwell fma.rn.f32x2): one issue slot performs two IEEE FMAs.  The forward is
+// issue bound (ncu: 73 % issue-active, 50 % FMA pipe), so halving the instruction count of the
+// 64 -> 8 projection is worth more than anything else; per-element results are unchanged.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(f32x2 &acc, f32x2 a, f32x2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+// acc[p][h] = (row 2p, row 2p+1) of head h;  acc += W[h][n] * sn + W[h][n+1] * cs, sin term first.
+// Weights sit in shared memory transposed and duplicated: s_wt2[n][h] = {w, w}.
+template <int R>
+__device__ __forceinline__ void project(const float2 (*s_wt2)[kRelHeads], int n, const float (&sn)[R], const float (&cs)[R],
+                                        f32x2 (&acc)[R / 2][kRelHeads])
+{
+    f32x2 fs[R / 2], fc[R / 2];
+#pragma unroll
+    for (int p = 0; p < R / 2; ++p) {
+        fs[p] = pack2(sn[2 * p], sn[2 * p + 1]);
+        fc[p] = pack2(cs[2 * p], cs[2 * p + 1]);
+    }
+    const ulonglong2 *ws = reinterpret_cast<const ulonglong2 *>(&s_wt2[n][0]);
+    const ulonglong2 *wc = reinterpret_cast<const ulonglong2 *>(&s_wt2[n + 1][0]);
+#pragma unroll
+    for (int q = 0; q < kRelHeads / 2; ++q) {
+        const ulonglong2 w = ws[q];
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p) {
+            ffma2(acc[p][2 * q], w.x, fs[p]);
+            ffma2(acc[p][2 * q + 1], w.y, fs[p]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kRelHeads / 2; ++q) {
+        const ulonglong2 w = wc[q];
+#pragma unroll
+        for (int p = 0; p < R / 2; ++p) {
+            ffma2(acc[p][2 * q], w.x, fc[p]);
+            ffma2(acc[p][2 * q + 1], w.y, fc[p]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// forward: lanes = 32 consecutive tgt columns j, each thread walks kRowsPerThread src rows
+// forward.  CTA = 4 warps, tile = 32 tgt columns (lanes) x kFwdRowsPerCta src rows; each warp walks
+// its rows kRowsPerIter at a time.  src rows are staged once per CTA in shared memory.
+// relu_bits layout: [B][N1][ceil(N2/32)][H] words (the 8 heads of one (row, column word) contiguous).
 // ------------------------------------------------------------------------------------------------
 constexpr int kRelFwdWarps = 4;
-constexpr int kRelFwdRows = 16;  // rows per CTA (4 per warp)
+constexpr int kRowsPerIter = 4;
+constexpr int kFwdRowsPerWarp = 16;
+constexpr int kFwdRowsPerCta = kRelFwdWarps * kFwdRowsPerWarp;
 
 template <bool FAST>
 __global__ void __launch_bounds__(32 * kRelFwdWarps)
-rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ weight,
-               const float *__restrict__ bias, const float *__restrict__ dim_t, float scale, float eps,
-               const uint8_t *__restrict__ mask, float *__restrict__ out, uint32_t *__restrict__ relu_bits, int N1, int N2)
+rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ src_tab,
+               const float *__restrict__ tgt_tab, const float *__restrict__ weight, const float *__restrict__ bias,
+               const float *__restrict__ dim_t, float scale, float eps, const uint8_t *__restrict__ mask,
+               float *__restrict__ out, uint32_t *__restrict__ relu_bits, int N1, int N2)
 {
-    __shared__ __align__(16) float s_wt[kRelFeat][kRelHeads];  // transposed: [n][h]
+    constexpr int R = kRowsPerIter;
+    constexpr int kRowF = FAST ? kTab : 4;  // floats staged per src row
+    __shared__ __align__(16) float2 s_wt[kRelFeat][kRelHeads];  // transposed and duplicated: [n][h] = {w, w}
+    __shared__ __align__(16) float s_row[kFwdRowsPerCta][kRowF];
     __shared__ float s_bias[kRelHeads];
     __shared__ float s_d[kRelK], s_invd[kRelK];
+    __shared__ float s_tgt[FAST ? kTab : 1][32];  // FAST: tgt table of the CTA's columns, [field][lane]
 
-    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * 32 + lane;
+    const int b = blockIdx.z;
+    const int i_cta = blockIdx.y * kFwdRowsPerCta;
     for (int idx = tid; idx < kRelFeat * kRelHeads; idx += 32 * kRelFwdWarps) {
         const int h = idx / kRelFeat, n = idx - h * kRelFeat;
-        s_wt[n][h] = weight[idx];
+        const float wv = weight[idx];
+        s_wt[n][h] = make_float2(wv, wv);
     }
     if (tid < kRelHeads) s_bias[tid] = bias[tid];
     if (tid < kRelK) {
         s_d[tid] = dim_t[tid];
         s_invd[tid] = 1.0f / dim_t[tid];
     }
+    {
+        const float *rows = (FAST ? src_tab : src) + ((size_t)b * N1 + i_cta) * kRowF;
+        const int nvalid = min(kFwdRowsPerCta, N1 - i_cta) * kRowF;
+        float *flat = &s_row[0][0];
+        for (int idx = tid; idx < kFwdRowsPerCta * kRowF; idx += 32 * kRelFwdWarps) flat[idx] = idx < nvalid ? rows[idx] : 1.0f;
+    }
     __syncthreads();
 
-    const int b = blockIdx.z;
-    const int j = blockIdx.x * 32 + threadIdx.x;
+    const int j = blockIdx.x * 32 + lane;
     const bool jok = j < N2;
     const int nwords = (N2 + 31) >> 5;
-    const float4 tb = jok ? __ldg(reinterpret_cast<const float4 *>(tgt) + (long long)b * N2 + j)
-                          : make_float4(0.f, 0.f, 1.f, 1.f);
 
-    const int i_begin = blockIdx.y * kRelFwdRows;
-    for (int r = threadIdx.y; r < kRelFwdRows; r += kRelFwdWarps) {
-        const int i = i_begin + r;
-        if (i >= N1) break;  // warp-uniform
-        const float4 sb = __ldg(reinterpret_cast<const float4 *>(src) + (long long)b * N1 + i);
-        float e[4];
-        pair_features(sb, tb, eps, e);
-        float acc[kRelHeads];
+    // per-column constants.  FAST: the tgt table rows of the CTA's 32 columns live in shared memory
+    // transposed ([field][lane], conflict-free) so the (c, k) loops below can stay rolled: fully
+    // unrolled, this kernel is ~55 KB of SASS and stalls on instruction fetch (ncu: "no instruction").
+    float x2 = 0.f, y2 = 0.f, w2e = 1.f, h2e = 1.f;
+    if constexpr (FAST) {
+        const float *trow = tgt_tab + ((size_t)b * N2 + (jok ? j : 0)) * kTab;
+        for (int f = warp; f < kTab; f += kRelFwdWarps) s_tgt[f][lane] = __ldg(trow + f);
+        __syncthreads();
+        x2 = s_tgt[0][lane];
+        y2 = s_tgt[1][lane];
+    } else {
+        const float4 tb = jok ? __ldg(reinterpret_cast<const float4 *>(tgt) + (size_t)b * N2 + j) : make_float4(0.f, 0.f, 1.f, 1.f);
+        x2 = tb.x; y2 = tb.y; w2e = tb.z + eps; h2e = tb.w + eps;
+    }
+
+    for (int r0 = 0; r0 < kFwdRowsPerWarp; r0 += R) {
+        const int lrow = warp * kFwdRowsPerWarp + r0;  // row inside the CTA tile
+        const int i0 = i_cta + lrow;
+        if (i0 >= N1) break;  // warp-uniform
+
+        f32x2 acc[R / 2][kRelHeads];
 #pragma unroll
-        for (int h = 0; h < kRelHeads; ++h) acc[h] = s_bias[h];
+        for (int p = 0; p < R / 2; ++p)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float es = e[c] * scale;  // (x * scale) first, position_encoding.py:133
+            for (int h = 0; h < kRelHeads; ++h) acc[p][h] = pack2(s_bias[h], s_bias[h]);
+
+        // ---- centre features c = 0, 1 ----
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            const float t_xy = c == 0 ? x2 : y2;
+            float es[R];
 #pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float *row = s_row[lrow + r];
+                float e;
+                if constexpr (FAST) e = logf(fabsf(row[c] - t_xy) * row[2 + c] + 1.0f);
+                else e = logf(fabsf(row[c] - t_xy) / (row[2 + c] + eps) + 1.0f);
+                es[r] = e * scale;  // (x * scale) first, position_encoding.py:133
+            }
+#pragma unroll 2
             for (int k = 0; k < kRelK; ++k) {
-                float sn, cs;
-                angle_sincos<FAST>(es, s_d[k], s_invd[k], sn, cs);
-                const int n = c * 2 * kRelK + 2 * k;
-                const float4 ws0 = *reinterpret_cast<const float4 *>(&s_wt[n][0]);
-                const float4 ws1 = *reinterpret_cast<const float4 *>(&s_wt[n][4]);
-                const float4 wc0 = *reinterpret_cast<const float4 *>(&s_wt[n + 1][0]);
-                const float4 wc1 = *reinterpret_cast<const float4 *>(&s_wt[n + 1][4]);
-                acc[0] = fmaf(ws0.x, sn, acc[0]); acc[1] = fmaf(ws0.y, sn, acc[1]);
-                acc[2] = fmaf(ws0.z, sn, acc[2]); acc[3] = fmaf(ws0.w, sn, acc[3]);
-                acc[4] = fmaf(ws1.x, sn, acc[4]); acc[5] = fmaf(ws1.y, sn, acc[5]);
-                acc[6] = fmaf(ws1.z, sn, acc[6]); acc[7] = fmaf(ws1.w, sn, acc[7]);
-                acc[0] = fmaf(wc0.x, cs, acc[0]); acc[1] = fmaf(wc0.y, cs, acc[1]);
-                acc[2] = fmaf(wc0.z, cs, acc[2]); acc[3] = fmaf(wc0.w, cs, acc[3]);
-                acc[4] = fmaf(wc1.x, cs, acc[4]); acc[5] = fmaf(wc1.y, cs, acc[5]);
-                acc[6] = fmaf(wc1.z, cs, acc[6]); acc[7] = fmaf(wc1.w, cs, acc[7]);
+                float sn[R], cs[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) angle_sincos<FAST>(es[r], s_d[k], s_invd[k], sn[r], cs[r]);
+                project<R>(s_wt, c * 2 * kRelK + 2 * k, sn, cs, acc);
             }
         }
-        const bool blocked = mask != nullptr && jok && mask[(long long)i * N2 + j] != 0;
+        // ---- size features c = 2, 3 ----
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            if constexpr (FAST) {
+#pragma unroll 2
+                for (int k = 0; k < kRelK; ++k) {
+                    const float sBk = s_tgt[4 + c * 8 + k][lane], cBk = s_tgt[20 + c * 8 + k][lane];
+                    float sn[R], cs[R];
 #pragma unroll
-        for (int h = 0; h < kRelHeads; ++h) {
-            const bool pos = jok && acc[h] > 0.f;
-            const long long row = ((long long)b * kRelHeads + h) * N1 + i;
-            if (relu_bits != nullptr) {
-                const uint32_t bits = __ballot_sync(0xffffffffu, pos);
-                if (threadIdx.x == 0) relu_bits[row * nwords + blockIdx.x] = bits;
+                    for (int r = 0; r < R; ++r) {
+                        const float sA = s_row[lrow + r][4 + c * 8 + k], cA = s_row[lrow + r][20 + c * 8 + k];
+                        sn[r] = fmaf(sA, cBk, -(cA * sBk));  // sin(A - B)
+                        cs[r] = fmaf(cA, cBk, sA * sBk);     // cos(A - B)
+                    }
+                    project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+                }
+            } else {
+                const float t_den = c == 0 ? w2e : h2e;
+                float es[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) es[r] = logf((s_row[lrow + r][2 + c] + eps) / t_den) * scale;
+#pragma unroll 2
+                for (int k = 0; k < kRelK; ++k) {
+                    float sn[R], cs[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) angle_sincos<false>(es[r], s_d[k], s_invd[k], sn[r], cs[r]);
+                    project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+                }
             }
-            if (jok) out[row * N2 + j] = blocked ? -INFINITY : (pos ? acc[h] : 0.f);
+        }
+
+        // ---- epilogue: ReLU, optional -inf mask, 1-bit sign record ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = i0 + r;
+            if (i >= N1) break;  // warp-uniform
+            const bool blocked = mask != nullptr && jok && mask[(size_t)i * N2 + j] != 0;
+            uint32_t words[kRelHeads];
+#pragma unroll
+            for (int h = 0; h < kRelHeads; ++h) {
+                float lo, hi;
+                unpack2(acc[r >> 1][h], lo, hi);
+                const float a = (r & 1) ? hi : lo;
+                const bool pos = jok && a > 0.f;
+                words[h] = __ballot_sync(0xffffffffu, pos);
+                if (jok) out[(((size_t)b * kRelHeads + h) * N1 + i) * N2 + j] = blocked ? -INFINITY : (pos ? a : 0.f);
+            }
+            if (relu_bits != nullptr && lane == 0) {
+                uint4 *dst = reinterpret_cast<uint4 *>(relu_bits + (((size_t)b * N1 + i) * nwords + blockIdx.x) * kRelHeads);
+                dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: grad_weight[h,n] = sum_pairs G[h] f[n], grad_bias[h] = sum_pairs G[h]
-// A CTA owns a tile of 32 columns x kRelBwdRows rows.  Its 8 warps all walk the same pairs; warp w
-// owns the feature chunk (box feature c = w/2, frequencies k = 4*(w%2) .. +3) => 8 features x 8
-// heads = 64 accumulators per lane.  Lanes = columns, so grad_out / relu_bits reads are coalesced.
+// backward: grad_weight[h,n] = sum_pairs G[h] f[n], grad_bias[h] = sum_pairs G[h], G = grad_out * bit.
+// CTA = 8 warps, tile = 32 columns (lanes) x kBwdRowsPerCta rows.  All warps walk the same pairs; warp
+// w owns the feature chunk (box feature c = w/2, frequencies k = 4*(w%2) .. +3) => 8 features x 8
+// heads = 64 accumulators per lane.  The gradient tile (8 heads x kBwdTileRows x 32) and its ReLU words are
+// staged once per CTA in shared memory with cp.async (each element read from HBM exactly once,
+// coalesced, double buffered), so the 8 warps read it with conflict-free LDS instead of eight
+// redundant global loads.
 // One shuffle tree + 64 atomics per warp at the end.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRelBwdWarps = 8;
-constexpr int kRelBwdRows = 64;
+constexpr int kBwdRowsPerCta = 64;
+constexpr int kBwdTileRows = 16;
 
 template <bool FAST>
-__global__ void __launch_bounds__(32 * kRelBwdWarps)
-rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ dim_t, float scale,
-               float eps, const float *__restrict__ grad_out, const uint32_t *__restrict__ relu_bits,
-               float *__restrict__ grad_weight, float *__restrict__ grad_bias, int N1, int N2)
+__global__ void __launch_bounds__(32 * kRelBwdWarps, 2)
+rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, const float *__restrict__ src_tab,
+               const float *__restrict__ tgt_tab, const float *__restrict__ dim_t, float scale, float eps,
+               const float *__restrict__ grad_out, const uint32_t *__restrict__ relu_bits, float *__restrict__ grad_weight,
+               float *__restrict__ grad_bias, int N1, int N2)
 {
+    constexpr int kRowF = FAST ? kTab : 4;
+    __shared__ __align__(16) float s_g[2][kBwdTileRows][kRelHeads][32];
+    __shared__ uint32_t s_bits[2][kBwdTileRows][kRelHeads];
+    __shared__ __align__(16) float s_row[kBwdRowsPerCta][kRowF];  // rows >= nrows hold 1.0 (harmless geometry)
+
     const int lane = threadIdx.x;
     const int w = threadIdx.y;
-    const int c = w >> 1;
+    const int tid = w * 32 + lane;
+    const int c = w >> 1;  // box feature of this warp
     const int k0 = (w & 1) * 4;
     const int b = blockIdx.z;
     const int j = blockIdx.x * 32 + lane;
     const bool jok = j < N2;
     const int nwords = (N2 + 31) >> 5;
+    const int i_cta = blockIdx.y * kBwdRowsPerCta;
+    const int nrows = min(kBwdRowsPerCta, N1 - i_cta);
+
+    {
+        const float *rows = (FAST ? src_tab : src) + ((size_t)b * N1 + i_cta) * kRowF;
+        float *flat = &s_row[0][0];
+        for (int idx = tid; idx < kBwdRowsPerCta * kRowF; idx += 32 * kRelBwdWarps) flat[idx] = idx < nrows * kRowF ? rows[idx] : 1.0f;
+    }
 
     float d[4], invd[4];
 #pragma unroll
@@ -178,8 +346,22 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
         d[k] = __ldg(dim_t + k0 + k);
         invd[k] = 1.0f / d[k];
     }
-    const float4 tb = jok ? __ldg(reinterpret_cast<const float4 *>(tgt) + (long long)b * N2 + j)
-                          : make_float4(0.f, 0.f, 1.f, 1.f);
+    // per-column constants of this warp's feature
+    float t_xy = 0.f, t_den = 1.f;  // centre coordinate / (size + eps) of the tgt box for feature c
+    float sB[4], cB[4];
+    if constexpr (FAST) {
+        const float *trow = tgt_tab + ((size_t)b * N2 + (jok ? j : 0)) * kTab;
+        t_xy = __ldg(trow + (c & 1));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sB[k] = __ldg(trow + 4 + (c & 1) * 8 + k0 + k);
+            cB[k] = __ldg(trow + 20 + (c & 1) * 8 + k0 + k);
+        }
+    } else {
+        const float4 tb = jok ? __ldg(reinterpret_cast<const float4 *>(tgt) + (size_t)b * N2 + j) : make_float4(0.f, 0.f, 1.f, 1.f);
+        t_xy = (c & 1) ? tb.y : tb.x;
+        t_den = ((c & 1) ? tb.w : tb.z) + eps;
+    }
 
     float acc[kRelHeads][8];
     float accb[kRelHeads];
@@ -190,24 +372,84 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
         for (int n = 0; n < 8; ++n) acc[h][n] = 0.f;
     }
 
-    const int i_begin = blockIdx.y * kRelBwdRows;
-    const int i_end = min(i_begin + kRelBwdRows, N1);
-    for (int i = i_begin; i < i_end; ++i) {
-        const float4 sb = __ldg(reinterpret_cast<const float4 *>(src) + (long long)b * N1 + i);
-        const float es = pair_feature(c, sb, tb, eps) * scale;
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) angle_sincos<FAST>(es, d[k], invd[k], f[2 * k], f[2 * k + 1]);
-#pragma unroll
-        for (int h = 0; h < kRelHeads; ++h) {
-            const long long row = ((long long)b * kRelHeads + h) * N1 + i;
-            const uint32_t bits = __ldg(relu_bits + row * nwords + blockIdx.x);
-            float g = 0.f;
-            if (jok && ((bits >> lane) & 1u)) g = ld_stream_f1(grad_out + row * N2 + j);
-#pragma unroll
-            for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g, f[n], acc[h][n]);
-            accb[h] += g;
+    // Tiles of kBwdTileRows rows of grad_out (8 heads x 32 columns) and their ReLU words are copied
+    // global -> shared with cp.async, double buffered: the copy of tile t+1 is in flight while tile t
+    // is consumed (ncu on the single-buffered version: long-scoreboard + barrier stalls dominate).
+    auto issue_tile = [&](int t0, int buf) {
+        const int trows = min(kBwdTileRows, nrows - t0);
+        for (int r = 0; r < kBwdTileRows; ++r) {
+            float *dst = &s_g[buf][r][w][lane];
+            if (r < trows && jok) {
+                const float *gsrc = grad_out + (((size_t)b * kRelHeads + w) * N1 + (i_cta + t0 + r)) * N2 + j;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(gsrc) : "memory");
+            } else {
+                *dst = 0.f;
+            }
         }
+        if (tid < kBwdTileRows * kRelHeads) {
+            const int r = tid >> 3, h = tid & 7;
+            uint32_t *dst = &s_bits[buf][r][h];
+            if (r < trows) {
+                const uint32_t *bsrc = relu_bits + (((size_t)b * N1 + (i_cta + t0 + r)) * nwords + blockIdx.x) * kRelHeads + h;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(bsrc) : "memory");
+            } else {
+                *dst = 0u;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue_tile(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < nrows; t0 += kBwdTileRows, buf ^= 1) {
+        const int trows = min(kBwdTileRows, nrows - t0);
+        if (t0 + kBwdTileRows < nrows) {
+            issue_tile(t0 + kBwdTileRows, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // tile `buf` (and, on the first pass, s_row) visible to every warp
+
+        // two rows per iteration: two independent feature chains in flight per lane (the kernel is
+        // latency bound at 2 CTAs/SM otherwise); rows past `trows` read zeroed s_g / padded s_row
+        for (int r = 0; r < trows; r += 2) {
+            float f[2][8];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float *row = s_row[t0 + r + u];
+                if constexpr (FAST) {
+                    if (c < 2) {
+                        const float es = logf(fabsf(row[c] - t_xy) * row[2 + c] + 1.0f) * scale;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) angle_sincos<true>(es, d[k], invd[k], f[u][2 * k], f[u][2 * k + 1]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float sA = row[4 + (c & 1) * 8 + k0 + k], cA = row[20 + (c & 1) * 8 + k0 + k];
+                            f[u][2 * k] = fmaf(sA, cB[k], -(cA * sB[k]));
+                            f[u][2 * k + 1] = fmaf(cA, cB[k], sA * sB[k]);
+                        }
+                    }
+                } else {
+                    float e;
+                    if (c < 2) e = logf(fabsf(row[c] - t_xy) / (row[2 + c] + eps) + 1.0f);
+                    else e = logf((row[c] + eps) / t_den);
+                    const float es = e * scale;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) angle_sincos<false>(es, d[k], invd[k], f[u][2 * k], f[u][2 * k + 1]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < kRelHeads; ++h) {
+                const float g0 = ((s_bits[buf][r][h] >> lane) & 1u) ? s_g[buf][r][h][lane] : 0.f;
+                const float g1 = ((s_bits[buf][r + 1][h] >> lane) & 1u) ? s_g[buf][r + 1][h][lane] : 0.f;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g1, f[1][n], fmaf(g0, f[0][n], acc[h][n]));
+                accb[h] += g0 + g1;
+            }
+        }
+        __syncthreads();  // every warp is done with tile `buf` before the copy after next overwrites it
     }
 
     // reduce over the 32 columns, then one atomic per (h, n) and warp
@@ -238,36 +480,68 @@ static int validate_rel(const char *who, int B, int N1, int N2, int H, int flags
     return RDETR_OK;
 }
 
+// FAST mode: fills the per-box tables in `workspace` ([B*N1 + B*N2] rows of kTab floats)
+static int prepare_tables(const char *who, const float *src, const float *tgt, const float *dim_t, float scale, float eps,
+                          int B, int N1, int N2, void *workspace, size_t workspace_bytes, cudaStream_t st,
+                          const float **src_tab, const float **tgt_tab)
+{
+    const size_t need = rdetr_relation_workspace_bytes(B, N1, N2, RDETR_REL_FAST);
+    if (!workspace || workspace_bytes < need)
+        return fail(RDETR_ERR_WORKSPACE, "%s: FAST mode needs a workspace of %zu bytes, got %zu", who, need, workspace ? workspace_bytes : (size_t)0);
+    if ((uintptr_t)workspace & 15) return fail(RDETR_ERR_INVALID_ARGUMENT, "%s: workspace must be 16-byte aligned", who);
+    float *ts = static_cast<float *>(workspace);
+    float *tt = ts + (size_t)B * N1 * kTab;
+    const int ns = B * N1, nt = B * N2;
+    rel_tables_kernel<<<(ns * 8 + 127) / 128, 128, 0, st>>>(src, dim_t, scale, eps, ts, ns);
+    rel_tables_kernel<<<(nt * 8 + 127) / 128, 128, 0, st>>>(tgt, dim_t, scale, eps, tt, nt);
+    *src_tab = ts;
+    *tgt_tab = tt;
+    return check_cuda(cudaGetLastError(), "rel_tables_kernel launch");
+}
+
 }  // namespace rdetr
+
+extern "C" size_t rdetr_relation_workspace_bytes(int B, int N1, int N2, int flags)
+{
+    if (flags != RDETR_REL_FAST || B <= 0) return 0;
+    return ((size_t)B * (size_t)(N1 > 0 ? N1 : 0) + (size_t)B * (size_t)(N2 > 0 ? N2 : 0)) * rdetr::kTab * sizeof(float);
+}
 
 extern "C" int rdetr_relation_forward(const float *src_boxes, const float *tgt_boxes, const float *weight, const float *bias,
                                       const float *dim_t, float scale, float eps, const uint8_t *attn_mask, float *out,
-                                      uint32_t *relu_bits, int B, int N1, int N2, int H, int flags, rdetr_stream_t stream)
+                                      uint32_t *relu_bits, int B, int N1, int N2, int H, int flags, void *workspace,
+                                      size_t workspace_bytes, rdetr_stream_t stream)
 {
     using namespace rdetr;
     if (int rc = validate_rel("rdetr_relation_forward", B, N1, N2, H, flags)) return rc;
     if (B == 0 || N1 == 0 || N2 == 0) return RDETR_OK;
     if (!src_boxes || !tgt_boxes || !weight || !bias || !dim_t || !out)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_forward: null pointer argument");
-    if (((uintptr_t)src_boxes | (uintptr_t)tgt_boxes) & 15)
-        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_forward: boxes must be 16-byte aligned");
+    if (((uintptr_t)src_boxes | (uintptr_t)tgt_boxes | (uintptr_t)relu_bits) & 15)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_forward: boxes / relu_bits must be 16-byte aligned");
     if (int rc = enter_device_of(out)) return rc;
     const dim3 block(32, kRelFwdWarps);
-    const dim3 grid((N2 + 31) / 32, (N1 + kRelFwdRows - 1) / kRelFwdRows, B);
+    const dim3 grid((N2 + 31) / 32, (N1 + kFwdRowsPerCta - 1) / kFwdRowsPerCta, B);
     if (grid.y > 65535) return fail(RDETR_ERR_UNSUPPORTED, "rdetr_relation_forward: N1=%d too large", N1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (flags == RDETR_REL_FAST)
-        rel_fwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, out,
+    if (flags == RDETR_REL_FAST) {
+        const float *ts = nullptr, *tt = nullptr;
+        if (int rc = prepare_tables("rdetr_relation_forward", src_boxes, tgt_boxes, dim_t, scale, eps, B, N1, N2, workspace,
+                                    workspace_bytes, st, &ts, &tt))
+            return rc;
+        rel_fwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, ts, tt, weight, bias, dim_t, scale, eps, attn_mask, out,
                                                      relu_bits, N1, N2);
-    else
-        rel_fwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, out,
-                                                      relu_bits, N1, N2);
+    } else {
+        rel_fwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, nullptr, nullptr, weight, bias, dim_t, scale, eps,
+                                                      attn_mask, out, relu_bits, N1, N2);
+    }
     return check_cuda(cudaGetLastError(), "rel_fwd_kernel launch");
 }
 
 extern "C" int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, const float *dim_t, float scale,
                                        float eps, const float *grad_out, const uint32_t *relu_bits, float *grad_weight,
-                                       float *grad_bias, int B, int N1, int N2, int H, int flags, rdetr_stream_t stream)
+                                       float *grad_bias, int B, int N1, int N2, int H, int flags, void *workspace,
+                                       size_t workspace_bytes, rdetr_stream_t stream)
 {
     using namespace rdetr;
     if (int rc = validate_rel("rdetr_relation_backward", B, N1, N2, H, flags)) return rc;
@@ -282,13 +556,18 @@ extern "C" int rdetr_relation_backward(const float *src_boxes, const float *tgt_
     if (((uintptr_t)src_boxes | (uintptr_t)tgt_boxes) & 15)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_backward: boxes must be 16-byte aligned");
     const dim3 block(32, kRelBwdWarps);
-    const dim3 grid((N2 + 31) / 32, (N1 + kRelBwdRows - 1) / kRelBwdRows, B);
+    const dim3 grid((N2 + 31) / 32, (N1 + kBwdRowsPerCta - 1) / kBwdRowsPerCta, B);
     if (grid.y > 65535) return fail(RDETR_ERR_UNSUPPORTED, "rdetr_relation_backward: N1=%d too large", N1);
-    if (flags == RDETR_REL_FAST)
-        rel_bwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, dim_t, scale, eps, grad_out, relu_bits, grad_weight,
-                                                     grad_bias, N1, N2);
-    else
-        rel_bwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, dim_t, scale, eps, grad_out, relu_bits, grad_weight,
-                                                      grad_bias, N1, N2);
+    if (flags == RDETR_REL_FAST) {
+        const float *ts = nullptr, *tt = nullptr;
+        if (int rc = prepare_tables("rdetr_relation_backward", src_boxes, tgt_boxes, dim_t, scale, eps, B, N1, N2, workspace,
+                                    workspace_bytes, st, &ts, &tt))
+            return rc;
+        rel_bwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, ts, tt, dim_t, scale, eps, grad_out, relu_bits,
+                                                     grad_weight, grad_bias, N1, N2);
+    } else {
+        rel_bwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, nullptr, nullptr, dim_t, scale, eps, grad_out,
+                                                      relu_bits, grad_weight, grad_bias, N1, N2);
+    }
     return check_cuda(cudaGetLastError(), "rel_bwd_kernel launch");
 }

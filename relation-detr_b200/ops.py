@@ -178,11 +178,15 @@ def relation_forward(src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias:
         _require(attn_mask.is_cuda and attn_mask.dtype == torch.bool and attn_mask.is_contiguous()
                  and attn_mask.shape == (N1, N2), "attn_mask must be a contiguous CUDA bool tensor of shape [N1, N2]")
     out = torch.empty((B, H, N1, N2), dtype=torch.float32, device=src_boxes.device)
-    bits = torch.empty((B, H, N1, (N2 + 31) // 32), dtype=torch.int32, device=src_boxes.device)
+    bits = torch.empty((B, N1, (N2 + 31) // 32, H), dtype=torch.int32, device=src_boxes.device)
+    flags = _lib.REL_FAST if fast else _lib.REL_EXACT
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_relation_workspace_bytes(B, N1, N2, flags)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=src_boxes.device) if ws_bytes else None
     with torch.cuda.device(src_boxes.device):
-        rc = _lib.lib().rdetr_relation_forward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(weight), _ptr(bias), _ptr(dim_t),
-                                               float(scale), float(eps), _ptr(attn_mask), _ptr(out), _ptr(bits),
-                                               B, N1, N2, H, _lib.REL_FAST if fast else _lib.REL_EXACT, _stream(src_boxes))
+        rc = L_.rdetr_relation_forward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(weight), _ptr(bias), _ptr(dim_t),
+                                       float(scale), float(eps), _ptr(attn_mask), _ptr(out), _ptr(bits),
+                                       B, N1, N2, H, flags, _ptr(ws), ws_bytes, _stream(src_boxes))
     _lib.check(rc, "rdetr_relation_forward")
     return out, bits
 
@@ -191,7 +195,7 @@ def relation_forward(src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias:
 def _(src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, fast):
     B, N1, N2, H = src_boxes.shape[0], src_boxes.shape[1], tgt_boxes.shape[1], bias.shape[0]
     return (src_boxes.new_empty((B, H, N1, N2)),
-            torch.empty((B, H, N1, (N2 + 31) // 32), dtype=torch.int32, device=src_boxes.device))
+            torch.empty((B, N1, (N2 + 31) // 32, H), dtype=torch.int32, device=src_boxes.device))
 
 
 @torch.library.custom_op("rdetr::relation_backward", mutates_args=(), device_types="cuda")
@@ -202,10 +206,14 @@ def relation_backward(src_boxes: Tensor, tgt_boxes: Tensor, dim_t: Tensor, scale
     _require(grad_out.shape == (B, num_heads, N1, N2), "grad_out must be [B, H, N1, N2]")
     gw = torch.empty((num_heads, 64), dtype=torch.float32, device=src_boxes.device)  # zeroed inside the library
     gb = torch.empty((num_heads,), dtype=torch.float32, device=src_boxes.device)
+    flags = _lib.REL_FAST if fast else _lib.REL_EXACT
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_relation_workspace_bytes(B, N1, N2, flags)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=src_boxes.device) if ws_bytes else None
     with torch.cuda.device(src_boxes.device):
-        rc = _lib.lib().rdetr_relation_backward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(dim_t), float(scale), float(eps),
-                                                _ptr(grad_out), _ptr(relu_bits), _ptr(gw), _ptr(gb), B, N1, N2, num_heads,
-                                                _lib.REL_FAST if fast else _lib.REL_EXACT, _stream(src_boxes))
+        rc = L_.rdetr_relation_backward(_ptr(src_boxes), _ptr(tgt_boxes), _ptr(dim_t), float(scale), float(eps),
+                                        _ptr(grad_out), _ptr(relu_bits), _ptr(gw), _ptr(gb), B, N1, N2, num_heads,
+                                        flags, _ptr(ws), ws_bytes, _stream(src_boxes))
     _lib.check(rc, "rdetr_relation_backward")
     return gw, gb
 

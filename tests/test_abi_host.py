@@ -43,10 +43,11 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     assert rc == 2 and b"D=16" in L.rdetr_last_error()
     rc = L.rdetr_msda_forward(None, None, None, None, None, None, 1, 10, 8, 32, 1, 1, 4, 0, None)
     assert rc == 1 and b"null" in L.rdetr_last_error()
-    rc = L.rdetr_relation_forward(None, None, None, None, None, 100.0, 1e-5, None, None, None, 1, 4, 4, 6, 0, None)
+    rc = L.rdetr_relation_forward(None, None, None, None, None, 100.0, 1e-5, None, None, None, 1, 4, 4, 6, 0, None, 0, None)
     assert rc == 2 and b"H=6" in L.rdetr_last_error()
     assert L.rdetr_msda_backward_workspace_bytes(2, 10, 8, 32, 1, 1, 4, 1) == 2 * 10 * 8 * 32 * 4
     assert L.rdetr_msda_backward_workspace_bytes(2, 10, 8, 32, 1, 1, 4, 0) == 0
+    assert L.rdetr_relation_workspace_bytes(2, 10, 6, 1) == 2 * 16 * 36 * 4 and L.rdetr_relation_workspace_bytes(2, 10, 6, 0) == 0
     with pytest.raises(_lib.RdetrOpsError):
         _lib.check(2, "x")
 
@@ -81,7 +82,7 @@ def test_fake_kernels_give_shapes_and_dtypes():
     tgt = torch.empty(2, 70, 4, device="meta")
     w, b, d = torch.empty(8, 64, device="meta"), torch.empty(8, device="meta"), torch.empty(8, device="meta")
     out, bits = torch.ops.rdetr.relation_forward(src, tgt, w, b, d, 100.0, 1e-5, None, False)
-    assert out.shape == (2, 8, 37, 70) and bits.shape == (2, 8, 37, 3) and bits.dtype == torch.int32
+    assert out.shape == (2, 8, 37, 70) and bits.shape == (2, 37, 3, 8) and bits.dtype == torch.int32
     gw, gb = torch.ops.rdetr.relation_backward(src, tgt, d, 100.0, 1e-5, out, bits, 8, False)
     assert gw.shape == (8, 64) and gb.shape == (8,)
 

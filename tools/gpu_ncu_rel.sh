@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+TAG=${1:-rel}
+timeout 300 python tools/profile_ops.py rel --iters 2 > gpurun_out/plain_profile.log 2>&1 &&
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'rel_fwd|rel_bwd' -c 8 -f -o gpurun_out/prof_${TAG} python tools/profile_ops.py rel --iters 2 > gpurun_out/ncu_full.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/ncu_full.log
