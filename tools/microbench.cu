@@ -99,6 +99,40 @@ __global__ void smem_rows(int nrows, int iters, float* sink)
     if (tab[threadIdx.x] == -1.f) sink[0] = 1.f;
 }
 
+// TMA reduce-add: each 8-lane group stages one 128-byte row in shared memory and one lane issues
+// cp.reduce.async.bulk (.add.f32) of 128 bytes to a random global row.  Moves the scatter off the LSU/L1 path.
+template <int DEPTH>
+__global__ void tma_red_rows(float* table, uint32_t nrows, int iters)
+{
+    extern __shared__ __align__(128) float stage[];  // [warps][DEPTH][4 groups][32 floats]
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    const uint32_t group = tid / 8, g = lane >> 3, l8 = lane & 7;
+    float* mystage = stage + (size_t)warp_in_cta * DEPTH * 4 * 32;
+    uint32_t seed = group * 2654435761u + 777u;
+    int slot = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+            seed = hash32(seed + u);
+            const uint32_t row = seed % nrows;
+            if (l8 == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DEPTH - 1) : "memory");
+            __syncwarp();
+            float* dst = mystage + (slot * 4 + g) * 32;
+            *reinterpret_cast<float4*>(dst + l8 * 4) = make_float4(1.f, 1.f, 1.f, 1.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (l8 == 0) {
+                const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(table + (size_t)row * 32), "r"(saddr) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            slot = (slot + 1) % DEPTH;
+        }
+    }
+    if (l8 == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 __global__ void ffma_chain(int iters, float* sink, float a, float b)
 {
     float x[16];
@@ -216,6 +250,15 @@ int main()
         ms = time_ms([&] { red_rows<1><<<blocks, threads>>>(ftab, c.rows, it2); });
         rows = nthreads / 32 * it2 * 8;
         printf("atomicAdd f32 128B rows, %-33s : %8.3f ms  %7.2f Grows/s  %7.2f TB/s\n", c.name, ms, rows / ms / 1e6, rows * 128 / ms / 1e9);
+    }
+    for (auto& c : rcfgs) {
+        const int it2 = 16;
+        constexpr int DEPTH = 4;
+        const size_t smem = (size_t)(threads / 32) * DEPTH * 4 * 32 * sizeof(float);
+        CK(cudaFuncSetAttribute(tma_red_rows<DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float ms = time_ms([&] { tma_red_rows<DEPTH><<<blocks, threads, smem>>>(ftab, c.rows, it2); });
+        double rows = nthreads / 8 * it2 * 8;
+        printf("TMA cp.reduce.async.bulk 128B rows, %-22s : %8.3f ms  %7.2f Grows/s  %7.2f TB/s\n", c.name, ms, rows / ms / 1e6, rows * 128 / ms / 1e9);
     }
     {
         const int nrows = 1024;  // 128 KB table per CTA
