@@ -120,6 +120,8 @@ def time_cpu_port(steps: int, warmup: int, sample_batch: int = 1, loc_kind: str 
     import torch
     from relation_detr_b200 import workloads
 
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it is allowed
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     full = workloads.MSDA_SHAPES[WORKLOAD]
     shape = workloads.MsdaShape(full.name, sample_batch, full.levels, 0)
     inp = workloads.make_msda_inputs(shape, loc_kind, seed=0, device="cpu")
@@ -152,7 +154,7 @@ def run_reference(args):
         "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "torch_threads": cores, "host_cpus": len(os.sched_getaffinity(0)),
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -329,7 +331,7 @@ def run_ours(args):
                     "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "MultiScaleDeformableAttnFunction.apply + autograd, pinned host buffers"},
             "gpu_launches": 2 * args.steps, "clocks": clocks, "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as tdist
         tdist.barrier()
@@ -337,7 +339,33 @@ def run_ours(args):
     return 0
 
 
+class RealStdout:
+    """Routes fd 1 to stderr while the benchmark runs (NCCL prints its version banner on stdout) and
+    keeps the original stdout for the single JSON line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.fd = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text: str):
+        os.write(self.fd, (text + "\n").encode())
+
+
+REAL_STDOUT = None
+
+
+def emit(line: dict):
+    text = json.dumps(line)
+    if REAL_STDOUT is not None:
+        REAL_STDOUT.emit(text)
+    else:
+        print(text)
+
+
 def main():
+    global REAL_STDOUT
+    REAL_STDOUT = RealStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
