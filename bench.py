@@ -185,40 +185,31 @@ def time_msda(torch, ops, inp, steps, warmup, dtype):
 
 
 def time_e2e(torch, rd, inp, steps, warmup):
-    """Public API (MultiScaleDeformableAttnFunction.apply + autograd) with pinned host buffers:
-    H2D of value/loc/attn/grad_out and D2H of out + the three gradients inside the timed region."""
+    """Public host-buffer API (relation_detr_b200.hostpipe.MsdaHostPipeline ->
+    MultiScaleDeformableAttnFunction.apply + autograd): every step copies value/loc/attn/grad_out from
+    pinned host memory and copies out + the three gradients back to pinned host memory, all inside the
+    timed region; copies of neighbouring steps overlap the compute on separate streams."""
+    from relation_detr_b200.hostpipe import MsdaHostPipeline
+
     dev = inp["value"].device
     host = {k: inp[k].cpu().pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
-    ss, lsi = inp["spatial_shapes"], inp["level_start_index"]
-    res_host = None
-    h2d = sum(t.numel() * t.element_size() for t in host.values())
-
-    def step():
-        nonlocal res_host
-        v = host["value"].to(dev, non_blocking=True).requires_grad_(True)
-        loc = host["sampling_locations"].to(dev, non_blocking=True).requires_grad_(True)
-        attn = host["attention_weights"].to(dev, non_blocking=True).requires_grad_(True)
-        go = host["grad_output"].to(dev, non_blocking=True)
-        out = rd.MultiScaleDeformableAttnFunction.apply(v, ss, lsi, loc, attn, 64)
-        out.backward(go)
-        outs = (out.detach(), v.grad, loc.grad, attn.grad)
-        if res_host is None:
-            res_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs]
-        for h, t in zip(res_host, outs):
-            h.copy_(t, non_blocking=True)
-        return sum(t.numel() * t.element_size() for t in outs)
-
-    d2h = 0
-    for _ in range(warmup):
-        d2h = step()
+    pipe = MsdaHostPipeline(inp["spatial_shapes"], inp["level_start_index"], dev)
+    for _ in range(max(warmup, 2)):
+        pipe.submit(host)
+    pipe.wait()
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(pipe.s_in)
     for _ in range(steps):
-        d2h = step()
-    e1.record()
+        res = pipe.submit(host)
+    e1.record(pipe.s_out)
+    pipe.wait()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps, h2d, d2h
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    ms = max(e0.elapsed_time(e1) / steps, 0.0)
+    assert torch.isfinite(res["out"][0, 0, 0])  # the result really is in host memory
+    return max(ms, wall_ms) if ms <= 0 else ms, pipe.h2d_bytes, pipe.d2h_bytes
 
 
 def time_rel(torch, ops, wl, name, steps, warmup, fast):
@@ -281,8 +272,8 @@ def run_ours(args):
     value = world * (fwd_b + bwd_b) / ms_max / 1e6  # GB/s, whole job
 
     # e2e through the public API with host buffers (fewer steps: PCIe-bound)
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_ms, h2d, d2h = time_e2e(torch, rd, inp, e2e_steps, 1)
+    e2e_steps = max(4, min(args.steps, 10))
+    e2e_ms, h2d, d2h = time_e2e(torch, rd, inp, e2e_steps, 2)
     e2e_ms_max = rdist.max_over_ranks(e2e_ms, dev)
     e2e_value = world * (fwd_b + bwd_b) / e2e_ms_max / 1e6
 
@@ -328,7 +319,7 @@ def run_ours(args):
                          "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4)},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "MultiScaleDeformableAttnFunction.apply + autograd, pinned host buffers"},
+                    "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "hostpipe.MsdaHostPipeline (MultiScaleDeformableAttnFunction.apply + autograd), pinned host buffers, copies overlapped across steps"},
             "gpu_launches": 2 * args.steps, "clocks": clocks, "extra": extra,
         }
         emit(line)
