@@ -264,3 +264,20 @@ def test_host_pipeline_matches_direct_call():
         assert np.allclose(res["grad_value"].numpy(), want["grad_value"], rtol=0, atol=1e-5)  # atomics: order differs
         assert np.array_equal(res["grad_attn"].numpy(), want["grad_attn"])
         assert np.array_equal(res["grad_loc"].numpy(), want["grad_loc"])
+
+
+def test_custom_op_registration_passes_opcheck():
+    """torch.library.opcheck: schema, fake kernel and autograd registration of the custom ops."""
+    shape = workloads.MsdaShape("t", 1, ((6, 9), (3, 5)), 11)
+    inp = workloads.make_msda_inputs(shape, "U", seed=2, device=DEV)
+    args = (inp["value"].requires_grad_(True), inp["spatial_shapes"], inp["level_start_index"],
+            inp["sampling_locations"].requires_grad_(True), inp["attention_weights"].requires_grad_(True))
+    torch.library.opcheck(torch.ops.rdetr.msda_forward.default, args,
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    r = workloads.make_rel_inputs(workloads.RelShape("t", 1, 9, 7), seed=1, device=DEV)
+    dim_t = ops.relation_dim_t(16, 10000.0, DEV)
+    for fast in (False, True):
+        torch.library.opcheck(torch.ops.rdetr.relation_forward.default,
+                              (r["src_boxes"], r["tgt_boxes"], r["weight"].requires_grad_(True), r["bias"].requires_grad_(True),
+                               dim_t, 100.0, 1e-5, None, fast),
+                              test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
