@@ -92,6 +92,35 @@ int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes,
                         rdetr_stream_t stream);
 
 /*
+ * Multi-scale deformable attention with the module prologue folded in ("N2"):
+ * softmax over the L*P logits of every (b, q, head), sampling location = reference point + offset, and
+ * the key-padding mask, which the reference computes with separate elementwise kernels before the op
+ * (models/bricks/ms_deform_attn.py:318-349).  Evaluation order follows torch:
+ *   attn = exp(z - max z) / sum;  ref_dim 2: loc = ref + off / (W_l, H_l);
+ *   ref_dim 4: loc = ref_xy + ((off / P) * ref_wh) * 0.5
+ *
+ *   reference_points  [B, Nq, L, ref_dim] fp32 (ref_dim 2 or 4; no gradient is produced for it: every
+ *                     call site of the reference passes detached / constant reference points)
+ *   sampling_offsets  [B, Nq, M, L, P, 2]   dtype     attention_logits [B, Nq, M, L*P] dtype (pre-softmax)
+ *   key_padding_mask  NULL or [B, S] bytes (torch.bool), non-zero = padded pixel, read as value 0
+ *   dtype             element type of value, out, offsets, logits and of all gradients
+ *   grad_offsets / grad_logits: every element is written; grad_value as in rdetr_msda_backward
+ *   workspace         rdetr_msda_backward_workspace_bytes(..., dtype) bytes
+ */
+int rdetr_msda_fused_forward(const void *value, const int64_t *spatial_shapes,
+                             const int64_t *level_start_index, const float *reference_points,
+                             const void *sampling_offsets, const void *attention_logits,
+                             const uint8_t *key_padding_mask, void *out, int B, int S, int M, int D,
+                             int L, int Nq, int P, int ref_dim, int dtype, rdetr_stream_t stream);
+int rdetr_msda_fused_backward(const void *value, const int64_t *spatial_shapes,
+                              const int64_t *level_start_index, const float *reference_points,
+                              const void *sampling_offsets, const void *attention_logits,
+                              const uint8_t *key_padding_mask, const void *grad_out, void *grad_value,
+                              void *grad_offsets, void *grad_logits, int B, int S, int M, int D, int L,
+                              int Nq, int P, int ref_dim, int dtype, void *workspace,
+                              size_t workspace_bytes, rdetr_stream_t stream);
+
+/*
  * Fused position-relation embedding, forward:
  *   out[b,h,i,j] = relu(bias[h] + sum_n weight[h,n] * f_n(src[b,i], tgt[b,j]))
  * with f = sin/cos encoding of the 4 log-ratio box features

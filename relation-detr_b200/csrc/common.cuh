@@ -187,6 +187,44 @@ __device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int st
     return t;
 }
 
+// ---- where phase 1 of the MSDA kernels gets a sample's (x, y, attention weight) from -------------
+// PlainIO: the reference's operator signature -- sampling_locations / attention_weights are tensors.
+// FusedIO: the module prologue folded into the kernel: softmax over the L*P logits
+// of a (b,q,m), loc = ref + off/(W,H) (2-d reference points) or ref_xy + off/P * ref_wh * 0.5 (4-d
+// boxes), and the key-padding mask, as models/bricks/ms_deform_attn.py:318-349 of the reference
+// computes them with separate elementwise kernels.  QT = dtype of offsets / logits and their grads.
+struct PlainIO {
+    static constexpr bool kFused = false;
+    const float *loc;
+    const float *attn;
+    float *grad_loc;
+    float *grad_attn;
+};
+
+template <typename QT>
+struct FusedIO {
+    static constexpr bool kFused = true;
+    const float *ref;        // [B, Nq, L, ref_dim] fp32
+    const QT *offsets;       // [B, Nq, M, L, P, 2]
+    const QT *logits;        // [B, Nq, M, L*P]
+    const uint8_t *mask;     // [B, S] or nullptr; non-zero = padded pixel (value treated as 0)
+    QT *grad_offsets;
+    QT *grad_logits;
+    int ref_dim;             // 2 or 4
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void from_f32(float &d, float v) { d = v; }
+__device__ __forceinline__ void from_f32(__nv_bfloat16 &d, float v) { d = __float2bfloat16_rn(v); }
+
+// sampling location of one sample from reference point + raw offset, evaluated in torch's order
+__device__ __forceinline__ float2 fused_location(const float *rp, int ref_dim, float offx, float offy, int W, int H, int P)
+{
+    if (ref_dim == 2) return make_float2(rp[0] + offx / (float)W, rp[1] + offy / (float)H);
+    return make_float2(rp[0] + ((offx / (float)P) * rp[2]) * 0.5f, rp[1] + ((offy / (float)P) * rp[3]) * 0.5f);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace rdetr

@@ -28,13 +28,11 @@ int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, in
 
 constexpr int kBwdThreads = 256;
 
-template <typename VT, int CH, int D>
+template <typename VT, int CH, int D, typename IO>
 __global__ void __launch_bounds__(kBwdThreads)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
-                const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
-                const float *__restrict__ attn, const VT *__restrict__ grad_out, float *__restrict__ grad_value_f32,
-                float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, int L, int Nq, int P,
-                long long total_pairs)
+                const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
+                float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs)
 {
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
@@ -62,15 +60,49 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     const int nsamples = npairs * LP;
 
     // ---- phase 1 -----------------------------------------------------------------------------------
-    const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + pair0 * LP;
-    const float *attn0 = attn + pair0 * LP;
+    float2 *s_stat = reinterpret_cast<float2 *>(s_meta + kPairs * stride);  // FusedIO: per-pair softmax statistics
+    if constexpr (IO::kFused) {
+        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
+            const int pair = s / LP;
+            s_meta[pair * stride + (s - pair * LP)].x = to_f32(io.logits[pair0 * LP + s]);
+        }
+        __syncthreads();
+        if (threadIdx.x < npairs) {
+            const float4 *row = s_meta + threadIdx.x * stride;
+            float mx = -INFINITY, sum = 0.f;
+            for (int lp = 0; lp < LP; ++lp) mx = fmaxf(mx, row[lp].x);
+            for (int lp = 0; lp < LP; ++lp) sum += expf(row[lp].x - mx);
+            s_stat[threadIdx.x] = make_float2(mx, sum);
+        }
+        __syncthreads();
+    }
     for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
         const int pair = s / LP;
         const int lp = s - pair * LP;
         const int l = lp / P;
-        const float2 xy = ld_stream_f2(loc2 + s);
-        const float a = ld_stream_f1(attn0 + s);
-        const Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        float2 xy;
+        float a;
+        long long bq = 0;
+        if constexpr (IO::kFused) {
+            const float2 st = s_stat[pair];
+            a = expf(s_meta[pair * stride + lp].x - st.x) / st.y;
+            bq = (pair0 + pair) / M;
+            const long long gs = pair0 * LP + s;
+            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, to_f32(io.offsets[2 * gs]),
+                                to_f32(io.offsets[2 * gs + 1]), s_W[l], s_H[l], P);
+        } else {
+            xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
+            a = ld_stream_f1(io.attn + pair0 * LP + s);
+        }
+        Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        if constexpr (IO::kFused) {
+            if (io.mask != nullptr) {
+                const uint8_t *mrow = io.mask + (bq / Nq) * (long long)S;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;
+            }
+        }
         s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
         s_meta[pair * stride + lp] = make_float4(t.lw, t.lh, a, 0.f);
     }
@@ -142,20 +174,51 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
             p_gw += __shfl_xor_sync(0xffffffffu, p_gw, off);
             p_gh += __shfl_xor_sync(0xffffffffu, p_gh, off);
         }
-        if (active && lane == 0) my_meta[lp] = make_float4(p_gw, p_gh, p_attn, 0.f);
+        if (active && lane == 0) my_meta[lp] = make_float4(p_gw, p_gh, p_attn, a);  // .w keeps the attention weight
     }
     __syncthreads();
 
-    // ---- phase 3: dense stores of grad_loc / grad_attn ----------------------------------------------
-    float2 *gl2 = reinterpret_cast<float2 *>(grad_loc) + pair0 * LP;
-    float *ga0 = grad_attn + pair0 * LP;
-    for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
-        const int pr = s / LP;
-        const int lp = s - pr * LP;
-        const int l = lp / P;
-        const float4 r = s_meta[pr * stride + lp];
-        gl2[s] = make_float2((float)s_W[l] * r.x, (float)s_H[l] * r.y);
-        ga0[s] = r.z;
+    // ---- phase 3: dense stores of the per-sample gradients -------------------------------------------
+    if constexpr (IO::kFused) {
+        // softmax backward needs sum_j a_j * dL/da_j of the pair; then chain through the location formula
+        if (threadIdx.x < npairs) {
+            const float4 *row = s_meta + threadIdx.x * stride;
+            float dot = 0.f;
+            for (int lp = 0; lp < LP; ++lp) dot = fmaf(row[lp].w, row[lp].z, dot);
+            s_stat[threadIdx.x].x = dot;
+        }
+        __syncthreads();
+        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
+            const int pr = s / LP;
+            const int lp = s - pr * LP;
+            const int l = lp / P;
+            const float4 r = s_meta[pr * stride + lp];
+            const long long gs = pair0 * LP + s;
+            const float glx = (float)s_W[l] * r.x, gly = (float)s_H[l] * r.y;  // d/d(loc), as the plain path returns it
+            float gox, goy;
+            if (io.ref_dim == 2) {
+                gox = glx / (float)s_W[l];
+                goy = gly / (float)s_H[l];
+            } else {
+                const float *rp = io.ref + (((pair0 + pr) / M) * L + l) * 4;
+                gox = ((glx * 0.5f) * rp[2]) / (float)P;
+                goy = ((gly * 0.5f) * rp[3]) / (float)P;
+            }
+            from_f32(io.grad_offsets[2 * gs], gox);
+            from_f32(io.grad_offsets[2 * gs + 1], goy);
+            from_f32(io.grad_logits[gs], r.w * (r.z - s_stat[pr].x));
+        }
+    } else {
+        float2 *gl2 = reinterpret_cast<float2 *>(io.grad_loc) + pair0 * LP;
+        float *ga0 = io.grad_attn + pair0 * LP;
+        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
+            const int pr = s / LP;
+            const int lp = s - pr * LP;
+            const int l = lp / P;
+            const float4 r = s_meta[pr * stride + lp];
+            gl2[s] = make_float2((float)s_W[l] * r.x, (float)s_H[l] * r.y);
+            ga0[s] = r.z;
+        }
     }
 }
 
@@ -173,17 +236,16 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
     reinterpret_cast<uint4 *>(dst)[i] = t;
 }
 
-template <typename VT, int CH>
-static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc, const float *attn,
-                      const void *grad_out, float *gv_f32, float *grad_loc, float *grad_attn, int B, int S, int M, int L,
-                      int Nq, int P, cudaStream_t stream)
+template <typename VT, int CH, typename IO>
+static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
+                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
     constexpr int kPairs = kBwdThreads / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
-    const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
-    auto kern = msda_bwd_kernel<VT, CH, D>;
+    const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
+    auto kern = msda_bwd_kernel<VT, CH, D, IO>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_bwd)"))
@@ -191,10 +253,32 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
     }
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
-    kern<<<(unsigned)grid, kBwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, loc, attn,
-                                                        static_cast<const VT *>(grad_out), gv_f32, grad_loc, grad_attn, S,
-                                                        M, L, Nq, P, total_pairs);
+    kern<<<(unsigned)grid, kBwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
+                                                        static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs);
     return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
+}
+
+// zero-fill of the fp32 accumulation target, the scatter kernel, and (bf16) the final conversion
+template <typename IOF32, typename IOBF16>
+static int run_backward(const void *value, const int64_t *shapes, const int64_t *lsi, const IOF32 &io32, const IOBF16 &io16,
+                        const void *grad_out, void *grad_value, int B, int S, int M, int D, int L, int Nq, int P, int dtype,
+                        void *workspace, cudaStream_t st)
+{
+    const size_t nvalue = (size_t)B * S * M * D;
+    float *acc = dtype == RDETR_DTYPE_F32 ? static_cast<float *>(grad_value) : static_cast<float *>(workspace);
+    if (int rc = check_cuda(cudaMemsetAsync(acc, 0, nvalue * sizeof(float), st), "cudaMemsetAsync(grad_value)")) return rc;
+    if (Nq > 0) {
+        const int rc = dtype == RDETR_DTYPE_F32
+                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, st)
+                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, st);
+        if (rc) return rc;
+    }
+    if (dtype == RDETR_DTYPE_BF16) {
+        const long long n8 = (long long)(nvalue / 8);  // D == 32 => divisible
+        f32_to_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(acc, static_cast<__nv_bfloat16 *>(grad_value), n8);
+        return check_cuda(cudaGetLastError(), "f32_to_bf16_kernel launch");
+    }
+    return RDETR_OK;
 }
 
 }  // namespace rdetr
@@ -228,23 +312,41 @@ extern "C" int rdetr_msda_backward(const void *value, const int64_t *spatial_sha
                     workspace ? workspace_bytes : (size_t)0);
     if (int rc = enter_device_of(value)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t nvalue = (size_t)B * S * M * D;
-    float *acc = value_dtype == RDETR_DTYPE_F32 ? static_cast<float *>(grad_value) : static_cast<float *>(workspace);
-    if (int rc = check_cuda(cudaMemsetAsync(acc, 0, nvalue * sizeof(float), st), "cudaMemsetAsync(grad_value)")) return rc;
-    if (Nq > 0) {
-        int rc;
-        if (value_dtype == RDETR_DTYPE_F32)
-            rc = launch_bwd<float, 4>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
-                                   grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
-        else
-            rc = launch_bwd<__nv_bfloat16, 4>(value, spatial_shapes, level_start_index, sampling_locations,
-                                           attention_weights, grad_out, acc, grad_loc, grad_attn, B, S, M, L, Nq, P, st);
-        if (rc) return rc;
-    }
-    if (value_dtype == RDETR_DTYPE_BF16) {
-        const long long n8 = (long long)(nvalue / 8);  // D == 32 => divisible
-        f32_to_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(acc, static_cast<__nv_bfloat16 *>(grad_value), n8);
-        return check_cuda(cudaGetLastError(), "f32_to_bf16_kernel launch");
-    }
-    return RDETR_OK;
+    const PlainIO io{sampling_locations, attention_weights, grad_loc, grad_attn};
+    return run_backward(value, spatial_shapes, level_start_index, io, io, grad_out, grad_value, B, S, M, D, L, Nq, P,
+                        value_dtype, workspace, st);
+}
+
+extern "C" int rdetr_msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                         const float *reference_points, const void *sampling_offsets,
+                                         const void *attention_logits, const uint8_t *key_padding_mask, const void *grad_out,
+                                         void *grad_value, void *grad_offsets, void *grad_logits, int B, int S, int M, int D,
+                                         int L, int Nq, int P, int ref_dim, int dtype, void *workspace, size_t workspace_bytes,
+                                         rdetr_stream_t stream)
+{
+    using namespace rdetr;
+    if (int rc = validate_msda("rdetr_msda_fused_backward", B, S, M, D, L, Nq, P, dtype)) return rc;
+    if (ref_dim != 2 && ref_dim != 4)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_backward: last dim of reference_points must be 2 or 4, got %d", ref_dim);
+    if (B == 0) return RDETR_OK;
+    if (!value || !spatial_shapes || !level_start_index || !grad_value)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_backward: null pointer argument");
+    if (Nq > 0 && (!reference_points || !sampling_offsets || !attention_logits || !grad_out || !grad_offsets || !grad_logits))
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_backward: null pointer argument");
+    if (((uintptr_t)value | (uintptr_t)grad_value | (uintptr_t)grad_out | (uintptr_t)workspace) & 15)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_backward: value/grad buffers must be 16-byte aligned");
+    const size_t need = rdetr_msda_backward_workspace_bytes(B, S, M, D, L, Nq, P, dtype);
+    if (need && (!workspace || workspace_bytes < need))
+        return fail(RDETR_ERR_WORKSPACE, "rdetr_msda_fused_backward: workspace of %zu bytes required, got %zu", need,
+                    workspace ? workspace_bytes : (size_t)0);
+    if (int rc = enter_device_of(value)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const FusedIO<float> io32{reference_points, static_cast<const float *>(sampling_offsets),
+                              static_cast<const float *>(attention_logits), key_padding_mask,
+                              static_cast<float *>(grad_offsets), static_cast<float *>(grad_logits), ref_dim};
+    const FusedIO<__nv_bfloat16> io16{reference_points, static_cast<const __nv_bfloat16 *>(sampling_offsets),
+                                      static_cast<const __nv_bfloat16 *>(attention_logits), key_padding_mask,
+                                      static_cast<__nv_bfloat16 *>(grad_offsets), static_cast<__nv_bfloat16 *>(grad_logits), ref_dim};
+    return run_backward(value, spatial_shapes, level_start_index, io32, io16, grad_out, grad_value, B, S, M, D, L, Nq, P, dtype,
+                        workspace, st);
 }

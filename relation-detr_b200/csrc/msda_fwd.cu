@@ -22,11 +22,10 @@ namespace rdetr {
 
 constexpr int kFwdThreads = 256;
 
-template <typename VT, int CH, int D>
+template <typename VT, int CH, int D, typename IO>
 __global__ void __launch_bounds__(kFwdThreads)
 msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
-                const int64_t *__restrict__ level_start_index, const float *__restrict__ loc,
-                const float *__restrict__ attn, VT *__restrict__ out, int S, int M, int L, int Nq,
+                const int64_t *__restrict__ level_start_index, const IO io, VT *__restrict__ out, int S, int M, int L, int Nq,
                 int P, long long total_pairs)
 {
     using SL = Slice<VT, CH>;
@@ -55,15 +54,49 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     // ---- phase 1: one thread per sample ----------------------------------------------------------
     const int nsamples = npairs * LP;
-    const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + pair0 * LP;
-    const float *attn0 = attn + pair0 * LP;
+    float2 *s_stat = reinterpret_cast<float2 *>(s_wgt + kPairs * stride);  // FusedIO: per-pair (max, sum) of the softmax
+    if constexpr (IO::kFused) {
+        for (int s = threadIdx.x; s < nsamples; s += kFwdThreads) {
+            const int pair = s / LP;
+            s_wgt[pair * stride + (s - pair * LP)].x = to_f32(io.logits[pair0 * LP + s]);
+        }
+        __syncthreads();
+        if (threadIdx.x < npairs) {
+            const float4 *row = s_wgt + threadIdx.x * stride;
+            float mx = -INFINITY, sum = 0.f;
+            for (int lp = 0; lp < LP; ++lp) mx = fmaxf(mx, row[lp].x);
+            for (int lp = 0; lp < LP; ++lp) sum += expf(row[lp].x - mx);
+            s_stat[threadIdx.x] = make_float2(mx, sum);
+        }
+        __syncthreads();
+    }
     for (int s = threadIdx.x; s < nsamples; s += kFwdThreads) {
         const int pair = s / LP;
         const int lp = s - pair * LP;
         const int l = lp / P;
-        const float2 xy = ld_stream_f2(loc2 + s);
-        const float a = ld_stream_f1(attn0 + s);
-        const Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        float2 xy;
+        float a;
+        long long bq = 0;
+        if constexpr (IO::kFused) {
+            const float2 st = s_stat[pair];
+            a = expf(s_wgt[pair * stride + lp].x - st.x) / st.y;  // softmax as torch evaluates it
+            bq = (pair0 + pair) / M;
+            const long long gs = pair0 * LP + s;
+            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, to_f32(io.offsets[2 * gs]),
+                                to_f32(io.offsets[2 * gs + 1]), s_W[l], s_H[l], P);
+        } else {
+            xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
+            a = ld_stream_f1(io.attn + pair0 * LP + s);
+        }
+        Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+        if constexpr (IO::kFused) {
+            if (io.mask != nullptr) {  // padded pixels read as zero (value.masked_fill of the reference, :318-319)
+                const uint8_t *mrow = io.mask + (bq / Nq) * (long long)S;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;
+            }
+        }
         const float hh = 1.f - t.lh, hw = 1.f - t.lw;
         s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
         s_wgt[pair * stride + lp] = make_float4(a * (hh * hw), a * (hh * t.lw), a * (t.lh * hw), a * (t.lh * t.lw));
@@ -108,17 +141,16 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     SL::store(out + gp * D + lane * kCh, acc);
 }
 
-template <typename VT, int CH>
-static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const float *loc,
-                      const float *attn, void *out, int B, int S, int M, int L, int Nq, int P,
-                      cudaStream_t stream)
+template <typename VT, int CH, typename IO>
+static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S,
+                      int M, int L, int Nq, int P, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
     constexpr int kPairs = kFwdThreads / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
-    const size_t smem = (size_t)kPairs * (L * P + 1) * 32;
-    auto kern = msda_fwd_kernel<VT, CH, D>;
+    const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
+    auto kern = msda_fwd_kernel<VT, CH, D, IO>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_fwd)"))
@@ -126,8 +158,8 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
     }
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_forward: B*Nq*M too large (%lld pairs)", total_pairs);
-    kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, loc, attn,
-                                                        static_cast<VT *>(out), S, M, L, Nq, P, total_pairs);
+    kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io, static_cast<VT *>(out),
+                                                        S, M, L, Nq, P, total_pairs);
     return check_cuda(cudaGetLastError(), "msda_fwd_kernel launch");
 }
 
@@ -162,9 +194,35 @@ extern "C" int rdetr_msda_forward(const void *value, const int64_t *spatial_shap
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_forward: value/out/loc/attn must be 16-byte aligned");
     if (int rc = enter_device_of(value)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PlainIO io{sampling_locations, attention_weights, nullptr, nullptr};
     if (value_dtype == RDETR_DTYPE_F32)
-        return launch_fwd<float, 4>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, out, B,
-                                 S, M, L, Nq, P, st);
-    return launch_fwd<__nv_bfloat16, 8>(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
-                                     out, B, S, M, L, Nq, P, st);
+        return launch_fwd<float, 4>(value, spatial_shapes, level_start_index, io, out, B, S, M, L, Nq, P, st);
+    return launch_fwd<__nv_bfloat16, 8>(value, spatial_shapes, level_start_index, io, out, B, S, M, L, Nq, P, st);
+}
+
+extern "C" int rdetr_msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                                        const float *reference_points, const void *sampling_offsets,
+                                        const void *attention_logits, const uint8_t *key_padding_mask, void *out, int B,
+                                        int S, int M, int D, int L, int Nq, int P, int ref_dim, int dtype,
+                                        rdetr_stream_t stream)
+{
+    using namespace rdetr;
+    if (int rc = validate_msda("rdetr_msda_fused_forward", B, S, M, D, L, Nq, P, dtype)) return rc;
+    if (ref_dim != 2 && ref_dim != 4)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_forward: last dim of reference_points must be 2 or 4, got %d", ref_dim);
+    if (B == 0 || Nq == 0) return RDETR_OK;
+    if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attention_logits || !out)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_forward: null pointer argument");
+    if (((uintptr_t)value | (uintptr_t)out) & 15)
+        return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_forward: value/out must be 16-byte aligned");
+    if (int rc = enter_device_of(value)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == RDETR_DTYPE_F32) {
+        const FusedIO<float> io{reference_points, static_cast<const float *>(sampling_offsets),
+                                static_cast<const float *>(attention_logits), key_padding_mask, nullptr, nullptr, ref_dim};
+        return launch_fwd<float, 4>(value, spatial_shapes, level_start_index, io, out, B, S, M, L, Nq, P, st);
+    }
+    const FusedIO<__nv_bfloat16> io{reference_points, static_cast<const __nv_bfloat16 *>(sampling_offsets),
+                                    static_cast<const __nv_bfloat16 *>(attention_logits), key_padding_mask, nullptr, nullptr, ref_dim};
+    return launch_fwd<__nv_bfloat16, 8>(value, spatial_shapes, level_start_index, io, out, B, S, M, L, Nq, P, st);
 }

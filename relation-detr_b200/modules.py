@@ -41,6 +41,9 @@ class MultiScaleDeformableAttention(nn.Module):
         # True: a bf16 value (autocast) is read as bf16 by the kernel, fp32 accumulation, bf16 out.
         # False: up-cast to fp32 first, exactly as the reference does (ms_deform_attn.py:360).
         self.native_bf16 = True
+        # True: softmax, location arithmetic and the padding mask run inside the kernel
+        # (rdetr_msda_fused_*); False: computed with torch ops before the call, as the reference does.
+        self.fused_prologue = True
         self.sampling_offsets = nn.Linear(embed_dim, num_heads * num_levels * num_points * 2)
         self.attention_weights = nn.Linear(embed_dim, num_heads * num_levels * num_points)
         self.value_proj = nn.Linear(embed_dim, embed_dim)
@@ -76,29 +79,37 @@ class MultiScaleDeformableAttention(nn.Module):
         S = value.shape[1]
         M, L, P = self.num_heads, self.num_levels, self.num_points
 
-        value = self.value_proj(value)
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], float(0))
-        value = value.view(B, S, M, self.embed_dim // M)
-
-        offsets = self.sampling_offsets(query).view(B, Nq, M, L, P, 2)
-        weights = self.attention_weights(query).view(B, Nq, M, L * P).softmax(-1).view(B, Nq, M, L, P)
-
-        if reference_points.shape[-1] == 2:
-            wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
-            locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 4:
-            locations = (reference_points[:, :, None, :, None, :2]
-                         + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
-        else:
+        if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
-
+        value = self.value_proj(value)
         in_dtype = value.dtype
         if not (self.native_bf16 and in_dtype == torch.bfloat16):
             value = value.to(torch.float32)
-        out = ops.MultiScaleDeformableAttnFunction.apply(
-            value.contiguous(), spatial_shapes, level_start_index,
-            locations.to(torch.float32).contiguous(), weights.to(torch.float32).contiguous(), self.im2col_step)
+        offsets = self.sampling_offsets(query).view(B, Nq, M, L, P, 2)
+        logits = self.attention_weights(query).view(B, Nq, M, L * P)
+
+        if self.fused_prologue:
+            if reference_points.requires_grad:
+                raise RuntimeError("the fused MSDA prologue produces no gradient for reference_points; detach them "
+                                   "(as every call site of the reference does) or set module.fused_prologue = False")
+            out = ops.ms_deform_attn_fused(
+                value.view(B, S, M, self.embed_dim // M), spatial_shapes, level_start_index,
+                reference_points.to(torch.float32).contiguous(), offsets.to(value.dtype).contiguous(),
+                logits.to(value.dtype).contiguous(), key_padding_mask)
+        else:
+            if key_padding_mask is not None:
+                value = value.masked_fill(key_padding_mask[..., None], float(0))
+            value = value.view(B, S, M, self.embed_dim // M)
+            weights = logits.softmax(-1).view(B, Nq, M, L, P)
+            if reference_points.shape[-1] == 2:
+                wh = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+                locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+            else:
+                locations = (reference_points[:, :, None, :, None, :2]
+                             + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+            out = ops.MultiScaleDeformableAttnFunction.apply(
+                value.contiguous(), spatial_shapes, level_start_index,
+                locations.to(torch.float32).contiguous(), weights.to(torch.float32).contiguous(), self.im2col_step)
         if out.dtype != in_dtype:
             out = out.to(in_dtype)
         return self.output_proj(out)

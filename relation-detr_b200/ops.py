@@ -23,6 +23,7 @@ from . import _lib
 
 __all__ = [
     "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
+    "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
 ]
 
@@ -146,6 +147,108 @@ class MultiScaleDeformableAttnFunction:
         # the reference rejects batches that are not a multiple of the step (ms_deform_attn_cuda.cu:44)
         _require(batch == 0 or (step > 0 and batch % step == 0), f"batch({batch}) must divide im2col_step({step})")
         return msda_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+
+
+# ---- MSDA with the module prologue fused (softmax, location arithmetic, padding mask) -------------
+
+def _check_fused(value, spatial_shapes, level_start_index, reference_points, offsets, logits, key_padding_mask):
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                    ("reference_points", reference_points), ("sampling_offsets", offsets), ("attention_logits", logits)):
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    _require(value.dim() == 4 and offsets.dim() == 6 and offsets.shape[-1] == 2, "value [B,S,M,D], sampling_offsets [B,Nq,M,L,P,2]")
+    B, S, M, D = value.shape
+    Bq, Nq, Mq, L, P, _ = offsets.shape
+    _require(B == Bq and M == Mq, "batch / head mismatch between value and sampling_offsets")
+    _require(logits.shape == (B, Nq, M, L * P), "attention_logits must be [B, Nq, M, L*P]")
+    _require(reference_points.dtype == torch.float32 and reference_points.dim() == 4
+             and reference_points.shape[:3] == (B, Nq, L), "reference_points must be fp32 [B, Nq, L, 2 or 4]")
+    R = reference_points.shape[-1]
+    if R not in (2, 4):
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(R))
+    _require(offsets.dtype == value.dtype and logits.dtype == value.dtype, "sampling_offsets / attention_logits must have value's dtype")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64
+             and spatial_shapes.shape == (L, 2) and level_start_index.shape == (L,), "spatial_shapes [L,2] / level_start_index [L] int64")
+    if key_padding_mask is not None:
+        _require(key_padding_mask.is_cuda and key_padding_mask.dtype == torch.bool and key_padding_mask.is_contiguous()
+                 and key_padding_mask.shape == (B, S), "key_padding_mask must be a contiguous CUDA bool tensor [B, S]")
+    return B, S, M, D, L, Nq, P, R
+
+
+@torch.library.custom_op("rdetr::msda_fused_forward", mutates_args=(), device_types="cuda")
+def msda_fused_forward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, reference_points: Tensor,
+                       sampling_offsets: Tensor, attention_logits: Tensor, key_padding_mask: Optional[Tensor]) -> Tensor:
+    B, S, M, D, L, Nq, P, R = _check_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                          attention_logits, key_padding_mask)
+    out = torch.empty((B, Nq, M * D), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().rdetr_msda_fused_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+                                                 _ptr(reference_points), _ptr(sampling_offsets), _ptr(attention_logits),
+                                                 _ptr(key_padding_mask), _ptr(out), B, S, M, D, L, Nq, P, R,
+                                                 _value_dtype_code(value), _stream(value))
+    _lib.check(rc, "rdetr_msda_fused_forward")
+    return out
+
+
+@msda_fused_forward.register_fake
+def _(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits, key_padding_mask):
+    B, _, M, D = value.shape
+    return value.new_empty((B, sampling_offsets.shape[1], M * D))
+
+
+@torch.library.custom_op("rdetr::msda_fused_backward", mutates_args=(), device_types="cuda")
+def msda_fused_backward(value: Tensor, spatial_shapes: Tensor, level_start_index: Tensor, reference_points: Tensor,
+                        sampling_offsets: Tensor, attention_logits: Tensor, key_padding_mask: Optional[Tensor],
+                        grad_output: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    B, S, M, D, L, Nq, P, R = _check_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                          attention_logits, key_padding_mask)
+    grad_output = grad_output.to(value.dtype).contiguous()
+    _require(grad_output.shape == (B, Nq, M * D), "grad_output must be [B, Nq, M*D]")
+    code = _value_dtype_code(value)
+    grad_value = torch.empty_like(value)
+    grad_offsets = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attention_logits)
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_msda_backward_workspace_bytes(B, S, M, D, L, Nq, P, code)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        rc = L_.rdetr_msda_fused_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(reference_points),
+                                          _ptr(sampling_offsets), _ptr(attention_logits), _ptr(key_padding_mask),
+                                          _ptr(grad_output), _ptr(grad_value), _ptr(grad_offsets), _ptr(grad_logits),
+                                          B, S, M, D, L, Nq, P, R, code, _ptr(ws), ws_bytes, _stream(value))
+    _lib.check(rc, "rdetr_msda_fused_backward")
+    return grad_value, grad_offsets, grad_logits
+
+
+@msda_fused_backward.register_fake
+def _(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits, key_padding_mask, grad_output):
+    return torch.empty_like(value), torch.empty_like(sampling_offsets), torch.empty_like(attention_logits)
+
+
+def _fused_setup_context(ctx, inputs, output):
+    value, spatial_shapes, level_start_index, reference_points, offsets, logits, mask = inputs
+    ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, offsets, logits)
+    ctx.mask = mask  # non-differentiable bool tensor
+
+
+def _fused_autograd_backward(ctx, grad_output):
+    value, spatial_shapes, level_start_index, reference_points, offsets, logits = ctx.saved_tensors
+    gv, go, gl = msda_fused_backward(value, spatial_shapes, level_start_index, reference_points, offsets, logits, ctx.mask,
+                                     grad_output)
+    # reference points are detached / constant at every call site of the reference
+    # (relation_transformer.py:337, base_transformer.py:57-75): no gradient is produced for them
+    return gv, None, None, None, go, gl, None
+
+
+msda_fused_forward.register_autograd(_fused_autograd_backward, setup_context=_fused_setup_context)
+
+
+def ms_deform_attn_fused(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits,
+                         key_padding_mask=None):
+    """value [B,S,M,D] (unmasked), reference_points [B,Nq,L,2|4] fp32, raw sampling_offsets [B,Nq,M,L,P,2] and
+    pre-softmax attention_logits [B,Nq,M,L*P] -> [B,Nq,M*D]; differentiable w.r.t. value, offsets, logits."""
+    return msda_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                              attention_logits, key_padding_mask)
 
 
 # ---- REL ----------------------------------------------------------------------------------------

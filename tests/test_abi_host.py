@@ -78,6 +78,13 @@ def test_fake_kernels_give_shapes_and_dtypes():
         assert out.shape == (B, Nq, M * D) and out.dtype == dt
         gv, gl, ga = torch.ops.rdetr.msda_backward(v, ss, lsi, loc, attn, out)
         assert gv.shape == v.shape and gv.dtype == dt and gl.shape == loc.shape and ga.shape == attn.shape
+        ref = torch.empty(B, Nq, L, 4, device="meta")
+        off = torch.empty(B, Nq, M, L, P, 2, dtype=dt, device="meta")
+        z = torch.empty(B, Nq, M, L * P, dtype=dt, device="meta")
+        out = torch.ops.rdetr.msda_fused_forward(v, ss, lsi, ref, off, z, None)
+        assert out.shape == (B, Nq, M * D) and out.dtype == dt
+        gv, go, gz = torch.ops.rdetr.msda_fused_backward(v, ss, lsi, ref, off, z, None, out)
+        assert gv.shape == v.shape and go.shape == off.shape and go.dtype == dt and gz.shape == z.shape
     src = torch.empty(2, 37, 4, device="meta")
     tgt = torch.empty(2, 70, 4, device="meta")
     w, b, d = torch.empty(8, 64, device="meta"), torch.empty(8, device="meta"), torch.empty(8, device="meta")

@@ -281,3 +281,121 @@ def test_custom_op_registration_passes_opcheck():
                               (r["src_boxes"], r["tgt_boxes"], r["weight"].requires_grad_(True), r["bias"].requires_grad_(True),
                                dim_t, 100.0, 1e-5, None, fast),
                               test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+# ---- fused prologue (softmax + location arithmetic + padding mask inside the kernel) ----------------
+
+def _fused_case(B, Nq, levels, M, P, ref_dim, seed, with_mask):
+    ss, lsi = workloads.shape_tensors(levels, DEV)
+    S, L = int(ss.prod(1).sum()), len(levels)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    value = torch.randn((B, S, M, 32), device=DEV, generator=g)
+    offsets = torch.randn((B, Nq, M, L, P, 2), device=DEV, generator=g) * 3.0
+    logits = torch.randn((B, Nq, M, L * P), device=DEV, generator=g) * 2.0
+    if ref_dim == 2:
+        ref = torch.rand((B, Nq, L, 2), device=DEV, generator=g) * 1.1 - 0.05
+    else:
+        ref = torch.cat([torch.rand((B, Nq, L, 2), device=DEV, generator=g),
+                         torch.rand((B, Nq, L, 2), device=DEV, generator=g) * 0.6 + 0.02], -1)
+    mask = (torch.rand((B, S), device=DEV, generator=g) > 0.8) if with_mask else None
+    go = torch.randn((B, Nq, M * 32), device=DEV, generator=g)
+    return value, ss, lsi, ref, offsets, logits, mask, go
+
+
+def _oracle_pipeline(value, ss, ref, offsets, logits, mask, go, dtype=torch.float64):
+    """The module prologue of the reference (ms_deform_attn.py:318-349) + the grid_sample oracle, in `dtype`."""
+    B, Nq, M, L, P, _ = offsets.shape
+    v = value.detach().to(dtype).clone().requires_grad_(True)
+    off = offsets.detach().to(dtype).clone().requires_grad_(True)
+    z = logits.detach().to(dtype).clone().requires_grad_(True)
+    vm = v if mask is None else v.masked_fill(mask[..., None, None], 0.0)
+    attn = z.softmax(-1).view(B, Nq, M, L, P)
+    r = ref.to(dtype)
+    if ref.shape[-1] == 2:
+        wh = torch.stack([ss[..., 1], ss[..., 0]], -1).to(dtype)
+        loc = r[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    else:
+        loc = r[:, :, None, :, None, :2] + off / P * r[:, :, None, :, None, 2:] * 0.5
+    out = torch_port.msda_grid_sample(vm, ss, loc, attn)
+    out.backward(go.to(dtype))
+    return out.detach(), v.grad, off.grad, z.grad
+
+
+@pytest.mark.parametrize("ref_dim,with_mask,levels,M,P", [
+    (2, False, ((13, 21), (7, 11), (4, 6), (2, 3)), 8, 4),
+    (4, True, ((13, 21), (7, 11), (4, 6), (2, 3)), 8, 4),
+    (2, True, ((9, 14), (5, 7), (3, 4), (2, 2), (1, 1)), 8, 4),
+    (4, False, ((6, 5), (3, 3)), 4, 2),
+    (2, False, ((7, 9),), 3, 1),
+])
+def test_fused_prologue_matches_oracle_pipeline(ref_dim, with_mask, levels, M, P):
+    value, ss, lsi, ref, offsets, logits, mask, go = _fused_case(2, 45, levels, M, P, ref_dim, 7, with_mask)
+    v = value.clone().requires_grad_(True)
+    off = offsets.clone().requires_grad_(True)
+    z = logits.clone().requires_grad_(True)
+    out = ops.ms_deform_attn_fused(v, ss, lsi, ref, off, z, mask)
+    out.backward(go)
+    want_out, want_gv, want_go, want_gz = _oracle_pipeline(value, ss, ref, offsets, logits, mask, go)
+    assert (out.double() - want_out).abs().max().item() <= 1e-5
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+    assert rel(v.grad, want_gv) <= 1e-4
+    assert rel(z.grad, want_gz) <= 1e-4
+    bad = ((off.grad.double() - want_go).abs() > 1e-4 * want_go.abs().max()).double().mean().item()
+    assert bad <= 2e-3, bad  # floor() flips only
+    if mask is not None:
+        assert torch.count_nonzero(v.grad[mask]) == 0  # padded pixels receive no gradient
+
+
+def test_fused_and_unfused_module_agree():
+    torch.manual_seed(0)
+    mod = rd.MultiScaleDeformableAttention(256, 4, 8, 4).to(DEV)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    levels = ((13, 21), (7, 11), (4, 6), (2, 3))
+    ss, lsi = workloads.shape_tensors(levels, DEV)
+    S = int(ss.prod(1).sum())
+    g = torch.Generator(device=DEV).manual_seed(3)
+    query = torch.randn((2, 50, 256), device=DEV, generator=g)
+    value = torch.randn((2, S, 256), device=DEV, generator=g)
+    mask = torch.rand((2, S), device=DEV, generator=g) > 0.85
+    for ref_dim in (2, 4):
+        refp = torch.rand((2, 50, 4, ref_dim), device=DEV, generator=g) * 0.5 + 0.2
+        grads = []
+        outs = []
+        for fused in (True, False):
+            mod.fused_prologue = fused
+            mod.zero_grad()
+            out = mod(query, refp, value, ss, lsi, mask)
+            out.square().sum().backward()
+            outs.append(out.detach())
+            grads.append({n: p.grad.clone() for n, p in mod.named_parameters()})
+        assert (outs[0] - outs[1]).abs().max().item() <= 1e-5
+        for n in grads[0]:
+            den = max(grads[1][n].abs().max().item(), 1e-6)
+            assert (grads[0][n] - grads[1][n]).abs().max().item() / den <= 2e-3, n
+    mod.fused_prologue = True
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ob = mod(query, refp, value, ss, lsi, mask)
+    assert ob.dtype == torch.bfloat16 and (ob.float() - outs[0]).abs().max().item() <= 0.1
+    with pytest.raises(RuntimeError, match="reference_points"):
+        mod(query, refp.clone().requires_grad_(True), value, ss, lsi, mask)
+
+
+def test_fused_bf16_and_opcheck():
+    value, ss, lsi, ref, offsets, logits, mask, go = _fused_case(1, 33, ((13, 21), (7, 11), (4, 6), (2, 3)), 8, 4, 2, 11, True)
+    vb, ob_, zb = value.bfloat16(), offsets.bfloat16(), logits.bfloat16()
+    v = vb.clone().requires_grad_(True)
+    off = ob_.clone().requires_grad_(True)
+    z = zb.clone().requires_grad_(True)
+    out = ops.ms_deform_attn_fused(v, ss, lsi, ref, off, z, mask)
+    out.backward(go.bfloat16())
+    want_out, want_gv, want_go, want_gz = _oracle_pipeline(vb.float(), ss, ref, ob_.float(), zb.float(), mask, go.bfloat16().float())
+    rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+    assert out.dtype == torch.bfloat16 and rel(out, want_out) <= 1e-2
+    assert rel(v.grad, want_gv) <= 2e-2 and rel(z.grad, want_gz) <= 2e-2
+    assert torch.isfinite(off.grad.float()).all()
+    args = (value[:, :, :, :].clone().requires_grad_(True), ss, lsi, ref, offsets.clone().requires_grad_(True),
+            logits.clone().requires_grad_(True), mask)
+    torch.library.opcheck(torch.ops.rdetr.msda_fused_forward.default, args,
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
