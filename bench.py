@@ -213,6 +213,42 @@ def time_e2e(torch, rd, inp, steps, warmup):
     return max(ms, wall_ms) if ms <= 0 else ms, pipe.h2d_bytes, pipe.d2h_bytes
 
 
+def measure_ceilings(torch, shape):
+    """Hardware rates that bind the two MSDA kernels, measured on this device with the library's diagnostic
+    micro-kernels (csrc/diag.cu): G rows/s of random 128-byte row gathers (forward pattern) and of 128-byte
+    vector reductions (backward pattern), over an L2-resident table (one image's value: 22 MB) and over a
+    table of the full batch's size (183 MB, exceeds what L2 keeps resident)."""
+    import ctypes
+
+    from relation_detr_b200 import _lib
+
+    L_ = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream().cuda_stream
+    sink = torch.zeros(16, device=dev)
+    out = {}
+    rows = ctypes.c_longlong(0)
+    for label, nrows in (("l2_resident", shape.S * shape.heads), ("batch_sized", shape.batch * shape.S * shape.heads)):
+        table = torch.zeros((nrows, 32), device=dev)
+        for kind in ("gather", "red"):
+            best = None
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if kind == "gather":
+                    rc = L_.rdetr_diag_gather_rows(table.data_ptr(), nrows, 32, sink.data_ptr(), ctypes.byref(rows), stream)
+                else:
+                    rc = L_.rdetr_diag_red_rows(table.data_ptr(), nrows, 16, ctypes.byref(rows), stream)
+                _lib.check(rc, "rdetr_diag")
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None else min(best, ms)
+            out[f"{kind}_Grows_per_s_{label}"] = round(rows.value / best / 1e6, 2)
+        del table
+    return out
+
+
 def time_rel(torch, ops, wl, name, steps, warmup, fast):
     shape = wl.REL_SHAPES[name]
     r = wl.make_rel_inputs(shape, seed=0, device="cuda")
@@ -271,6 +307,7 @@ def run_ours(args):
     fwd_max = rdist.max_over_ranks(fwd_ms, dev)
     bwd_max = rdist.max_over_ranks(bwd_ms, dev)
     value = world * (fwd_b + bwd_b) / ms_max / 1e6  # GB/s, whole job
+    corner_rows = shape.batch * shape.Nq * shape.heads * shape.L * shape.points * 4  # upper bound: all corners valid
 
     # e2e through the public API with host buffers (fewer steps: PCIe-bound)
     e2e_steps = max(4, min(args.steps, 10))
@@ -280,6 +317,7 @@ def run_ours(args):
 
     extra = {}
     cpu_baseline = None
+    ceilings = measure_ceilings(torch, shape) if rank == 0 else {}
     if rank == 0 and not args.quick:
         k, w = max(3, min(args.steps, 10)), 3
         other = "U" if args.loc == "S" else "S"
@@ -319,7 +357,16 @@ def run_ours(args):
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of msda_bwd_kernel per launch, ncu --set full, profiles/r01a_ncu_summary.md (loc S)",
                          "algorithmic_bytes": bwd_b, "peak_source": peak_src,
                          "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
-                         "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4)},
+                         "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4),
+                         # the resources that actually bind: one 128-byte row per bilinear corner
+                         "binding": {
+                             "corner_rows_per_launch": corner_rows,
+                             "fwd_gather_Grows_per_s": round(corner_rows / fwd_max / 1e6, 2),
+                             "bwd_red_Grows_per_s": round(corner_rows / bwd_max / 1e6, 2),
+                             "measured_ceilings": ceilings,
+                             "fwd_frac_of_l1_gather_ceiling": round(corner_rows / fwd_max / 1e6 / ceilings["gather_Grows_per_s_l2_resident"], 3) if ceilings else None,
+                             "bwd_frac_of_l2_atomic_ceiling": round(corner_rows / bwd_max / 1e6 / ceilings["red_Grows_per_s_l2_resident"], 3) if ceilings else None,
+                             "note": "fwd is L1-wavefront bound (one wavefront per corner row), bwd is L2-atomic-unit bound; neither can reach the HBM roofline with the reference's [B,S,M,D] layout"}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "hostpipe.MsdaHostPipeline (MultiScaleDeformableAttnFunction.apply + autograd), pinned host buffers, copies overlapped across steps"},

@@ -163,6 +163,17 @@ int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, cons
                             int N1, int N2, int H, int flags, void *workspace,
                             size_t workspace_bytes, rdetr_stream_t stream);
 
+/*
+ * Diagnostics (not on the product path): measure on the current device the two hardware rates that
+ * bound the MSDA kernels -- random 128-byte row gathers (8 lanes x 16-byte read-only loads per row) and
+ * 128-byte vector reductions (red.global.add.v4.f32) -- over a caller-provided table of nrows rows.
+ * The caller times the launch with CUDA events; *rows_out (host memory) receives the rows touched.
+ */
+int rdetr_diag_gather_rows(const void *table, long long nrows, int iters, float *sink,
+                           long long *rows_out, rdetr_stream_t stream);
+int rdetr_diag_red_rows(void *table, long long nrows, int iters, long long *rows_out,
+                        rdetr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDETR_OPS_LIB", os.path.join(PKG_DIR, "librdetr_ops.so"))
@@ -27,6 +27,8 @@ _SIGNATURES = {
     "rdetr_relation_workspace_bytes": (c_size_t, [c_int] * 4),
     "rdetr_relation_forward": (c_int, [c_void_p] * 5 + [c_float, c_float] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_relation_backward": (c_int, [c_void_p] * 3 + [c_float, c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "rdetr_diag_gather_rows": (c_int, [c_void_p, c_longlong, c_int, c_void_p, ctypes.POINTER(c_longlong), c_void_p]),
+    "rdetr_diag_red_rows": (c_int, [c_void_p, c_longlong, c_int, ctypes.POINTER(c_longlong), c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
