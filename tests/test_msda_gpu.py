@@ -399,3 +399,31 @@ def test_fused_bf16_and_opcheck():
             logits.clone().requires_grad_(True), mask)
     torch.library.opcheck(torch.ops.rdetr.msda_fused_forward.default, args,
                           test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_against_the_reference_cuda_extension_when_built():
+    """oracle/_ref = the reference's own ms_deform_attn_cuda.cu, unmodified, compiled for sm_100a
+    (oracle/build_ref_cuda.py).  Its fp64 run is a second, independent oracle on the GPU; its fp32 run is
+    the noise floor our fp32 kernel is compared with."""
+    from oracle import build_ref_cuda
+
+    refc = build_ref_cuda.load_prebuilt()
+    if refc is None:
+        pytest.skip("oracle/_ref not built (needs the reference tree; build container only)")
+    for kind, shape in (("oob", workloads.MsdaShape("t", 2, ((25, 42), (13, 21), (7, 11), (4, 6)), 300)),
+                        ("S", workloads.MSDA_SHAPES["msda_enc_800x1333_b1"])):
+        inp = workloads.make_msda_inputs(shape, kind, seed=4, device=DEV)
+        v, ss, lsi = inp["value"], inp["spatial_shapes"], inp["level_start_index"]
+        loc, attn, go = inp["sampling_locations"], inp["attention_weights"], inp["grad_output"]
+        out64 = refc.ms_deform_attn_forward(v.double(), ss, lsi, loc.double(), attn.double(), 64)
+        out32 = refc.ms_deform_attn_forward(v, ss, lsi, loc, attn, 64)
+        gv64, gl64, ga64 = refc.ms_deform_attn_backward(v.double(), ss, lsi, loc.double(), attn.double(), go.double(), 64)
+        out = ops.msda_forward(v, ss, lsi, loc, attn)
+        gv, gl, ga = ops.msda_backward(v, ss, lsi, loc, attn, go)
+        ours = (out.double() - out64).abs().max().item()
+        floor = (out32.double() - out64).abs().max().item()
+        assert ours <= max(1e-5, 1.5 * floor), (ours, floor)
+        rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max()).item()
+        assert rel(gv, gv64) <= 1e-4 and rel(ga, ga64) <= 1e-4
+        bad = ((gl.double() - gl64).abs() > 1e-4 * gl64.abs().max()).double().mean().item()
+        assert bad <= 1e-3, bad
