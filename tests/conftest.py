@@ -18,6 +18,10 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
 
+    # no GPU test may hang the box: hard per-test limit (pytest-timeout) unless the test sets its own
+    for item in items:
+        if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(600))
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device")

@@ -181,3 +181,17 @@ def test_workload_byte_counts_match_baseline_md():
     assert round(f16 / 1e6, 1) == 457.2 and round(b16 / 1e6, 1) == 822.9
     assert workloads.MSDA_SHAPES["msda_enc_1200x2000_b1"].S == 204098
     assert round(workloads.REL_SHAPES["rel_900_b8"].algorithmic_bytes()[0] / 1e6, 1) == 207.4
+
+
+def test_generators_are_deterministic_on_cpu():
+    a = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "D", seed=3)
+    b = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "D", seed=3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    r1 = workloads.make_rel_inputs(workloads.REL_SHAPES["rel_tiny"], seed=5)
+    r2 = workloads.make_rel_inputs(workloads.REL_SHAPES["rel_tiny"], seed=5)
+    assert all(torch.equal(r1[k], r2[k]) for k in r1)
+    strict = workloads.make_loc(workloads.MSDA_SHAPES["msda_tiny"], "strict", seed=1)
+    wh = torch.tensor([[w, h] for h, w in workloads.MSDA_SHAPES["msda_tiny"].levels], dtype=torch.float32)
+    px = strict * wh[None, None, None, :, None, :] - 0.5
+    frac = px - px.floor()
+    assert ((frac > 0.004) & (frac < 0.996)).all()  # the strict generator keeps samples off pixel boundaries

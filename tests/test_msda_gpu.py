@@ -427,3 +427,30 @@ def test_against_the_reference_cuda_extension_when_built():
         assert rel(gv, gv64) <= 1e-4 and rel(ga, ga64) <= 1e-4
         bad = ((gl.double() - gl64).abs() > 1e-4 * gl64.abs().max()).double().mean().item()
         assert bad <= 1e-3, bad
+
+
+@pytest.mark.parametrize("name,kind,nq", [("msda_dec_900_b8", "D", None), ("msda_dec_1100_b8", "D", None),
+                                          ("msda_dec_1500_b8", "D", None), ("msda_enc_1200x2000_b1", "S", 20000)])
+def test_config_shapes_against_gpu_oracle(name, kind, nq):
+    """The decoder shapes (Nq = 900 / 1100 / 1500 over the 800x1333 pyramid, B reduced to 2 for the oracle)
+    and the 5-level 1200x2000 pyramid (S = 204098, a strided 20000-query subset) vs the fp64 oracle."""
+    base = workloads.MSDA_SHAPES[name]
+    shape = workloads.MsdaShape(base.name, min(base.batch, 2), base.levels, nq or base.num_query)
+    inp = workloads.make_msda_inputs(shape, kind, seed=9, device=DEV)
+    ref = run_torch_oracle(inp, torch.float64)
+    ref32 = run_torch_oracle(inp, torch.float32)
+    r = run_ours(inp)
+    floor = maxabs(ref32["out"], ref["out"])
+    assert maxabs(r["out"], ref["out"]) <= max(1e-5, 1.5 * floor)
+    assert relmax(r["grad_value"], ref["grad_value"]) <= 1e-4
+    assert relmax(r["grad_attn"], ref["grad_attn"]) <= 1e-4
+    bad = np.abs(r["grad_loc"] - ref["grad_loc"]) > 1e-4 * np.abs(ref["grad_loc"]).max()
+    assert bad.mean() <= 1e-3
+
+
+def test_generators_are_deterministic():
+    a = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "S", seed=3, device=DEV)
+    b = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "S", seed=3, device=DEV)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    c = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "S", seed=4, device=DEV)
+    assert not torch.equal(a["value"], c["value"])

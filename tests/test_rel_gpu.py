@@ -55,7 +55,7 @@ def test_matches_reference_fixtures(name, fast):
     assert relmax(gb, g["ref64_grad_bias"]) <= gtol
 
 
-@pytest.mark.parametrize("B,N1,N2", [(1, 1, 1), (2, 37, 29), (1, 31, 33), (3, 64, 100), (1, 900, 900)])
+@pytest.mark.parametrize("B,N1,N2", [(1, 1, 1), (2, 37, 29), (1, 31, 33), (3, 64, 100), (1, 900, 900), (1, 1100, 1100)])
 def test_matches_c_oracle_on_seeded_inputs(B, N1, N2):
     r = workloads.make_rel_inputs(workloads.RelShape("t", B, N1, N2), seed=N1)
     src, tgt, w, b = (r[k] for k in ("src_boxes", "tgt_boxes", "weight", "bias"))

@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r01}
-echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q -s --timeout=600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_gpu.log
 echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 echo "== ncu launch list (bench --quick)"
 timeout 600 python bench.py --steps 3 --warmup 3 --quick --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 &&
