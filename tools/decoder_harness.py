@@ -39,8 +39,8 @@ def sine_embed(pos, feats=128, temperature=10000.0, scale=2 * math.pi):
     dim_t = temperature ** (torch.arange(feats // 2, dtype=torch.float32, device=pos.device) * 2 / feats)
     ang = pos.unsqueeze(-1) * scale / dim_t
     emb = torch.stack((ang.sin(), ang.cos()), dim=-1).flatten(-2)  # [..., 4, feats]
-    idx = torch.tensor([1, 0, 2, 3], device=pos.device)
-    return emb.index_select(-2, idx).flatten(-2)
+    # (y, x, w, h) order; sliced rather than index_select so the step stays CUDA-graph capturable
+    return torch.cat((emb[..., 1:2, :], emb[..., 0:1, :], emb[..., 2:, :]), dim=-2).flatten(-2)
 
 
 def inverse_sigmoid(x, eps=1e-3):
