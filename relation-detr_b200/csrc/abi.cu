@@ -23,18 +23,26 @@ int check_cuda(cudaError_t e, const char *what)
     return fail(RDETR_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
-int enter_device_of(const void *ptr)
+DeviceGuard::DeviceGuard(const void *ptr)
 {
     cudaPointerAttributes attr;
     cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
-    if (e != cudaSuccess) return check_cuda(e, "cudaPointerGetAttributes");
-    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
-        return fail(RDETR_ERR_INVALID_ARGUMENT, "buffer %p is not device memory (no CPU path exists in this library)", ptr);
-    int cur = -1;
-    e = cudaGetDevice(&cur);
-    if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice");
-    if (cur != attr.device) return check_cuda(cudaSetDevice(attr.device), "cudaSetDevice");
-    return RDETR_OK;
+    if (e != cudaSuccess) { rc_ = check_cuda(e, "cudaPointerGetAttributes"); return; }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) {
+        rc_ = fail(RDETR_ERR_INVALID_ARGUMENT, "buffer %p is not device memory (no CPU path exists in this library)", ptr);
+        return;
+    }
+    e = cudaGetDevice(&prev_);
+    if (e != cudaSuccess) { rc_ = check_cuda(e, "cudaGetDevice"); return; }
+    if (prev_ != attr.device) {
+        rc_ = check_cuda(cudaSetDevice(attr.device), "cudaSetDevice");
+        switched_ = rc_ == RDETR_OK;
+    }
+}
+
+DeviceGuard::~DeviceGuard()
+{
+    if (switched_) cudaSetDevice(prev_);
 }
 
 }  // namespace rdetr

@@ -16,9 +16,19 @@ namespace rdetr {
 // ---- host side ---------------------------------------------------------------------------------
 int fail(int code, const char *fmt, ...);  // records the thread-local message, returns `code`
 int check_cuda(cudaError_t e, const char *what);
-// Makes the device that owns `ptr` current for this thread (the reference has no device guard,
-// ms_deform_attn_cuda.cu:57; we derive the device from the data so multi-GPU callers are safe).
-int enter_device_of(const void *ptr);
+// Makes the device that owns `ptr` current for this thread for the lifetime of the guard and restores
+// the previous one afterwards (the reference has no device guard, ms_deform_attn_cuda.cu:57; we derive
+// the device from the data so multi-GPU callers are safe whatever their current device is).
+class DeviceGuard {
+public:
+    explicit DeviceGuard(const void *ptr);
+    ~DeviceGuard();
+    int status() const { return rc_; }  // RDETR_OK or an error code (message recorded)
+private:
+    int prev_ = -1;
+    bool switched_ = false;
+    int rc_ = 0;
+};
 
 constexpr int kMaxLevels = 8;
 constexpr int kMaxPoints = 8;

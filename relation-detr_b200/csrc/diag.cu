@@ -58,7 +58,8 @@ extern "C" int rdetr_diag_gather_rows(const void *table, long long nrows, int it
     using namespace rdetr;
     if (!table || !sink || nrows <= 0 || nrows > 0x7fffffffLL || iters <= 0 || ((uintptr_t)table & 15))
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_diag_gather_rows: bad argument");
-    if (int rc = enter_device_of(table)) return rc;
+    const DeviceGuard guard(table);
+    if (guard.status()) return guard.status();
     const int blocks = 148 * 16, threads = 256;
     diag_gather_rows_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4 *>(table),
                                                                                       (uint32_t)nrows, iters, sink);
@@ -71,7 +72,8 @@ extern "C" int rdetr_diag_red_rows(void *table, long long nrows, int iters, long
     using namespace rdetr;
     if (!table || nrows <= 0 || nrows > 0x7fffffffLL || iters <= 0 || ((uintptr_t)table & 15))
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_diag_red_rows: bad argument");
-    if (int rc = enter_device_of(table)) return rc;
+    const DeviceGuard guard(table);
+    if (guard.status()) return guard.status();
     const int blocks = 148 * 16, threads = 256;
     diag_red_rows_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float *>(table), (uint32_t)nrows, iters);
     if (rows_out) *rows_out = (long long)blocks * threads / 8 * iters * 8;

@@ -310,7 +310,8 @@ extern "C" int rdetr_msda_backward(const void *value, const int64_t *spatial_sha
     if (need && (!workspace || workspace_bytes < need))
         return fail(RDETR_ERR_WORKSPACE, "rdetr_msda_backward: workspace of %zu bytes required, got %zu", need,
                     workspace ? workspace_bytes : (size_t)0);
-    if (int rc = enter_device_of(value)) return rc;
+    const DeviceGuard guard(value);
+    if (guard.status()) return guard.status();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PlainIO io{sampling_locations, attention_weights, grad_loc, grad_attn};
     return run_backward(value, spatial_shapes, level_start_index, io, io, grad_out, grad_value, B, S, M, D, L, Nq, P,
@@ -339,7 +340,8 @@ extern "C" int rdetr_msda_fused_backward(const void *value, const int64_t *spati
     if (need && (!workspace || workspace_bytes < need))
         return fail(RDETR_ERR_WORKSPACE, "rdetr_msda_fused_backward: workspace of %zu bytes required, got %zu", need,
                     workspace ? workspace_bytes : (size_t)0);
-    if (int rc = enter_device_of(value)) return rc;
+    const DeviceGuard guard(value);
+    if (guard.status()) return guard.status();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const FusedIO<float> io32{reference_points, static_cast<const float *>(sampling_offsets),
                               static_cast<const float *>(attention_logits), key_padding_mask,

@@ -192,7 +192,8 @@ extern "C" int rdetr_msda_forward(const void *value, const int64_t *spatial_shap
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_forward: null pointer argument");
     if (((uintptr_t)value | (uintptr_t)out | (uintptr_t)sampling_locations | (uintptr_t)attention_weights) & 15)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_forward: value/out/loc/attn must be 16-byte aligned");
-    if (int rc = enter_device_of(value)) return rc;
+    const DeviceGuard guard(value);
+    if (guard.status()) return guard.status();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PlainIO io{sampling_locations, attention_weights, nullptr, nullptr};
     if (value_dtype == RDETR_DTYPE_F32)
@@ -215,7 +216,8 @@ extern "C" int rdetr_msda_fused_forward(const void *value, const int64_t *spatia
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_forward: null pointer argument");
     if (((uintptr_t)value | (uintptr_t)out) & 15)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_fused_forward: value/out must be 16-byte aligned");
-    if (int rc = enter_device_of(value)) return rc;
+    const DeviceGuard guard(value);
+    if (guard.status()) return guard.status();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype == RDETR_DTYPE_F32) {
         const FusedIO<float> io{reference_points, static_cast<const float *>(sampling_offsets),

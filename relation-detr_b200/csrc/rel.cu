@@ -519,7 +519,8 @@ extern "C" int rdetr_relation_forward(const float *src_boxes, const float *tgt_b
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_forward: null pointer argument");
     if (((uintptr_t)src_boxes | (uintptr_t)tgt_boxes | (uintptr_t)relu_bits) & 15)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_forward: boxes / relu_bits must be 16-byte aligned");
-    if (int rc = enter_device_of(out)) return rc;
+    const DeviceGuard guard(out);
+    if (guard.status()) return guard.status();
     const dim3 block(32, kRelFwdWarps);
     const dim3 grid((N2 + 31) / 32, (N1 + kFwdRowsPerCta - 1) / kFwdRowsPerCta, B);
     if (grid.y > 65535) return fail(RDETR_ERR_UNSUPPORTED, "rdetr_relation_forward: N1=%d too large", N1);
@@ -546,7 +547,8 @@ extern "C" int rdetr_relation_backward(const float *src_boxes, const float *tgt_
     using namespace rdetr;
     if (int rc = validate_rel("rdetr_relation_backward", B, N1, N2, H, flags)) return rc;
     if (!grad_weight || !grad_bias) return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_relation_backward: null gradient buffer");
-    if (int rc = enter_device_of(grad_weight)) return rc;
+    const DeviceGuard guard(grad_weight);
+    if (guard.status()) return guard.status();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (int rc = check_cuda(cudaMemsetAsync(grad_weight, 0, sizeof(float) * kRelHeads * kRelFeat, st), "cudaMemsetAsync(grad_weight)")) return rc;
     if (int rc = check_cuda(cudaMemsetAsync(grad_bias, 0, sizeof(float) * kRelHeads, st), "cudaMemsetAsync(grad_bias)")) return rc;

@@ -454,3 +454,32 @@ def test_generators_are_deterministic():
     assert all(torch.equal(a[k], b[k]) for k in a)
     c = workloads.make_msda_inputs(workloads.MSDA_SHAPES["msda_tiny"], "S", seed=4, device=DEV)
     assert not torch.equal(a["value"], c["value"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_non_current_device():
+    """The library derives the device from the data pointer and restores the caller's current device
+    (the reference kernel launches on whatever device is current, ms_deform_attn_cuda.cu:57)."""
+    import ctypes
+
+    from relation_detr_b200 import _lib
+
+    shape = workloads.MsdaShape("t", 1, ((13, 21), (7, 11)), 40)
+    inp0 = workloads.make_msda_inputs(shape, "U", seed=0, device="cuda:0")
+    inp1 = {k: v.to("cuda:1") for k, v in inp0.items()}
+    torch.cuda.set_device(0)
+    want = ops.msda_forward(inp0["value"], inp0["spatial_shapes"], inp0["level_start_index"], inp0["sampling_locations"],
+                            inp0["attention_weights"])
+    # raw C-ABI call with device 0 current and every buffer on device 1
+    out1 = torch.empty_like(inp1["value"][:, :40].reshape(1, 40, 256))
+    B, S, M, D = inp1["value"].shape
+    rc = _lib.lib().rdetr_msda_forward(inp1["value"].data_ptr(), inp1["spatial_shapes"].data_ptr(), inp1["level_start_index"].data_ptr(),
+                                       inp1["sampling_locations"].data_ptr(), inp1["attention_weights"].data_ptr(), out1.data_ptr(),
+                                       B, S, M, D, 2, 40, 4, 0, torch.cuda.current_stream(torch.device("cuda:1")).cuda_stream)
+    assert rc == 0
+    assert torch.cuda.current_device() == 0
+    torch.cuda.synchronize(1)
+    assert torch.equal(out1.cpu(), want.cpu())
+    got = ops.msda_forward(inp1["value"], inp1["spatial_shapes"], inp1["level_start_index"], inp1["sampling_locations"],
+                           inp1["attention_weights"])
+    assert got.device == torch.device("cuda:1") and torch.equal(got.cpu(), want.cpu())
