@@ -41,6 +41,15 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     # D = 16 is not supported: error code + message, no crash, no launch
     rc = L.rdetr_msda_forward(1, 1, 1, 1, 1, 1, 1, 10, 8, 16, 1, 1, 4, 0, None)
     assert rc == 2 and b"D=16" in L.rdetr_last_error()
+    # maximum sizes: S*M*D must fit 31 bits, at most 8 levels / 8 points, dtype 0 or 1
+    assert L.rdetr_msda_forward(1, 1, 1, 1, 1, 1, 1, 1 << 23, 8, 32, 4, 1, 4, 0, None) == 2 and b"31 bits" in L.rdetr_last_error()
+    assert L.rdetr_msda_forward(1, 1, 1, 1, 1, 1, 1, 10, 8, 32, 9, 1, 4, 0, None) == 2 and b"L=9" in L.rdetr_last_error()
+    assert L.rdetr_msda_forward(1, 1, 1, 1, 1, 1, 1, 10, 8, 32, 4, 1, 4, 7, None) == 2 and b"value_dtype 7" in L.rdetr_last_error()
+    assert L.rdetr_msda_fused_forward(1, 1, 1, 1, 1, 1, None, 1, 1, 10, 8, 32, 4, 1, 4, 3, 0, None) == 1 and b"2 or 4" in L.rdetr_last_error()
+    # empty batches / query sets are a no-op, not an error
+    assert L.rdetr_msda_forward(None, None, None, None, None, None, 0, 10, 8, 32, 4, 5, 4, 0, None) == 0
+    assert L.rdetr_msda_forward(None, None, None, None, None, None, 2, 10, 8, 32, 4, 0, 4, 0, None) == 0
+    assert L.rdetr_relation_forward(None, None, None, None, None, 100.0, 1e-5, None, None, None, 0, 4, 4, 8, 0, None, 0, None) == 0
     rc = L.rdetr_msda_forward(None, None, None, None, None, None, 1, 10, 8, 32, 1, 1, 4, 0, None)
     assert rc == 1 and b"null" in L.rdetr_last_error()
     rc = L.rdetr_relation_forward(None, None, None, None, None, 100.0, 1e-5, None, None, None, 1, 4, 4, 6, 0, None, 0, None)
