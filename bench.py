@@ -336,7 +336,7 @@ def run_ours(args):
             fb2, bb2 = s2.algorithmic_bytes(4)
             extra[f"{name}_f32_loc{kind}"] = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((fb2 + bb2) / t / 1e6, 1)}
             del d2
-        for name in ("rel_900_b8", "rel_1100_b8"):
+        for name in ("rel_900_b8", "rel_1100_b8", "rel_2900_b1"):
             extra[name + "_exact"] = time_rel(torch, ops, workloads, name, k, w, False)
             extra[name + "_fast"] = time_rel(torch, ops, workloads, name, k, w, True)
     if rank == 0 and not args.no_cpu_baseline:

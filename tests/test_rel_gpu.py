@@ -169,3 +169,22 @@ def test_full_size_properties():
     d = (fast - out).abs()
     print(f"\nREL fast-vs-exact at B=8,N=900: max {d.max().item():.2e} mean {d.mean().item():.2e}")
     assert d.max().item() <= 1e-4 and d.mean().item() <= 5e-6
+
+
+def test_focal_config_size_properties():
+    """B=1, N=2900 (focalnet config with denoising_nums=1000): sub-block consistency, mask fusion, backward."""
+    r = workloads.make_rel_inputs(workloads.REL_SHAPES["rel_2900_b1"], seed=0, device=DEV)
+    mask = workloads.cdn_attn_mask(900, 10, 200, DEV)  # 2000 dn rows + 900 queries
+    w = r["weight"].clone().requires_grad_(True)
+    b = r["bias"].clone().requires_grad_(True)
+    for fast in (False, True):
+        out = ops.position_relation_bias(r["src_boxes"], r["tgt_boxes"], w, b, attn_mask=mask, fast=fast)
+        assert out.shape == (1, 8, 2900, 2900)
+        assert torch.equal(torch.isneginf(out), mask[None, None].expand_as(out))
+        sub = ops.position_relation_bias(r["src_boxes"][:, 2000:2100].contiguous(), r["tgt_boxes"][:, 2500:2533].contiguous(),
+                                         w, b, fast=fast)
+        assert torch.equal(sub, out[:, :, 2000:2100, 2500:2533])
+        out.masked_fill(mask, 0.0).sum().backward()
+        assert torch.isfinite(w.grad).all() and w.grad.abs().sum() > 0
+        w.grad = None
+        b.grad = None
