@@ -124,3 +124,46 @@ def test_fixtures_are_reproducible_from_the_reference():
         mod.pos_proj[0].bias.copy_(torch.from_numpy(g["bias"]))
         out = mod(torch.from_numpy(g["src_boxes"]), torch.from_numpy(g["tgt_boxes"]))
     assert maxabs(out.numpy(), g["ref32_out"]) < 1e-6
+
+
+def test_two_restatements_agree_on_random_shapes():
+    """C restatement vs torch port (both pinned to the fixtures above) on 12 random configurations in
+    fp64, including D != 32, one-pixel levels and far out-of-range samples: <= 1e-11 everywhere."""
+    rng = np.random.default_rng(0)
+    for case in range(12):
+        L = int(rng.integers(1, 6))
+        levels = tuple((int(rng.integers(1, 12)), int(rng.integers(1, 14))) for _ in range(L))
+        B, M, D = int(rng.integers(1, 3)), int(rng.integers(1, 5)), int(rng.choice([4, 8, 32]))
+        P, Nq = int(rng.integers(1, 5)), int(rng.integers(1, 30))
+        S = sum(h * w for h, w in levels)
+        value = rng.standard_normal((B, S, M, D))
+        loc = rng.uniform(-0.6, 1.6, (B, Nq, M, L, P, 2))
+        attn = rng.uniform(0, 1, (B, Nq, M, L, P))
+        go = rng.standard_normal((B, Nq, M * D))
+        shapes = np.array(levels, dtype=np.int64)
+        lsi = np.concatenate([[0], np.cumsum(shapes.prod(1))[:-1]]).astype(np.int64)
+        out = c_oracle.msda_forward(value, shapes, lsi, loc, attn)
+        gv, gl, ga = c_oracle.msda_backward(value, shapes, lsi, loc, attn, go)
+        tv = torch.from_numpy(value).requires_grad_(True)
+        tl = torch.from_numpy(loc).requires_grad_(True)
+        ta = torch.from_numpy(attn).requires_grad_(True)
+        tout = torch_port.msda_grid_sample(tv, torch.from_numpy(shapes), tl, ta)
+        tout.backward(torch.from_numpy(go))
+        assert maxabs(out, tout.detach().numpy()) < 1e-11, case
+        assert maxabs(gv, tv.grad.numpy()) < 1e-11 and maxabs(ga, ta.grad.numpy()) < 1e-11, case
+        assert maxabs(gl, tl.grad.numpy()) < 1e-9, case
+    for case in range(6):
+        B, N1, N2 = int(rng.integers(1, 3)), int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        src = np.concatenate([rng.uniform(0, 1, (B, N1, 2)), rng.uniform(1e-3, 0.5, (B, N1, 2))], -1)
+        tgt = np.concatenate([rng.uniform(0, 1, (B, N2, 2)), rng.uniform(1e-3, 0.5, (B, N2, 2))], -1)
+        w, b = rng.uniform(-0.125, 0.125, (8, 64)), rng.uniform(-0.125, 0.125, 8)
+        dim_t = torch_port.relation_dim_t().numpy().astype(np.float64)
+        out = c_oracle.rel_forward(src, tgt, w, b, dim_t)
+        tw = torch.from_numpy(w).requires_grad_(True)
+        tb = torch.from_numpy(b).requires_grad_(True)
+        tout = torch_port.rel_eager(torch.from_numpy(src), torch.from_numpy(tgt), tw, tb, torch.from_numpy(dim_t))
+        go = rng.standard_normal(out.shape)
+        tout.backward(torch.from_numpy(go))
+        gw, gb = c_oracle.rel_backward(src, tgt, w, b, dim_t, go)
+        assert maxabs(out, tout.detach().numpy()) < 1e-11, case
+        assert maxabs(gw, tw.grad.numpy()) < 1e-9 and maxabs(gb, tb.grad.numpy()) < 1e-9, case
