@@ -236,7 +236,7 @@ def measure_ceilings(torch, shape):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 if kind == "gather":
-                    rc = L_.rdetr_diag_gather_rows(table.data_ptr(), nrows, 32, sink.data_ptr(), ctypes.byref(rows), stream)
+                    rc = L_.rdetr_diag_gather_rows(table.data_ptr(), nrows, 128, sink.data_ptr(), ctypes.byref(rows), stream)
                 else:
                     rc = L_.rdetr_diag_red_rows(table.data_ptr(), nrows, 16, ctypes.byref(rows), stream)
                 _lib.check(rc, "rdetr_diag")
@@ -366,7 +366,7 @@ def run_ours(args):
                              "measured_ceilings": ceilings,
                              "fwd_frac_of_l1_gather_ceiling": round(corner_rows / fwd_max / 1e6 / ceilings["gather_Grows_per_s_l2_resident"], 3) if ceilings else None,
                              "bwd_frac_of_l2_atomic_ceiling": round(corner_rows / bwd_max / 1e6 / ceilings["red_Grows_per_s_l2_resident"], 3) if ceilings else None,
-                             "note": "fwd is L1-wavefront bound (one wavefront per corner row), bwd is L2-atomic-unit bound; neither can reach the HBM roofline with the reference's [B,S,M,D] layout"}},
+                             "note": "fwd is bound by the L1 gather path (one 128-byte wavefront per corner row; latency-limited below the measured ceiling), bwd by the L2 atomic unit; neither can reach the HBM roofline with the reference's [B,S,M,D] layout"}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "hostpipe.MsdaHostPipeline (MultiScaleDeformableAttnFunction.apply + autograd), pinned host buffers, copies overlapped across steps"},

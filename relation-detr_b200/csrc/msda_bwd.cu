@@ -20,16 +20,16 @@
 // grad_value accumulates in fp32.  For bf16 value the accumulation target is an fp32 workspace that
 // a second kernel converts (bf16 accumulation would lose the small addends on coarse levels, where
 // one address receives ~1e3 updates).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rdetr {
 
 int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype);
 
-constexpr int kBwdThreads = 256;
-
-template <typename VT, int CH, int D, typename IO>
-__global__ void __launch_bounds__(kBwdThreads)
+template <typename VT, int CH, int D, typename IO, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
                 float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs)
@@ -37,6 +37,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
     constexpr int kLanes = D / kCh;
+    constexpr int kBwdThreads = THREADS;
     constexpr int kPairs = kBwdThreads / kLanes;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,16 +237,16 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
     reinterpret_cast<uint4 *>(dst)[i] = t;
 }
 
-template <typename VT, int CH, typename IO>
-static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
-                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
+template <typename VT, int CH, typename IO, int THREADS>
+static int launch_bwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
+                              float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
-    constexpr int kPairs = kBwdThreads / kLanes;
+    constexpr int kPairs = THREADS / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
-    auto kern = msda_bwd_kernel<VT, CH, D, IO>;
+    auto kern = msda_bwd_kernel<VT, CH, D, IO, THREADS>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_bwd)"))
@@ -253,9 +254,23 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
     }
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
-    kern<<<(unsigned)grid, kBwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
-                                                        static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs);
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
+                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs);
     return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
+}
+
+template <typename VT, int CH, typename IO>
+static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
+                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
+{
+#ifdef RDETR_TUNE_FWD
+    const char *e = getenv("RDETR_MSDA_BWD_VARIANT");
+    const int v = e ? atoi(e) : 0;
+    if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+#endif
+    // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls
+    return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
 }
 
 // zero-fill of the fp32 accumulation target, the scatter kernel, and (bf16) the final conversion

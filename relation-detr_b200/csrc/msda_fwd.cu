@@ -7,7 +7,8 @@
 // Layout of the work here:
 //   * a "pair" is one (b, q, m): its L*P samples are contiguous in sampling_locations and
 //     attention_weights, its D outputs are contiguous in `out`, and consecutive pairs are
-//     contiguous too, so a CTA that owns kPairs consecutive pairs streams three dense blocks;
+//     contiguous too, so a CTA that owns kPairs consecutive pairs (8 for fp32, 16 for bf16: 64 threads)
+//     streams three dense blocks;
 //   * phase 1 (one thread per sample): coalesced streaming loads of loc/attn, coordinate
 //     arithmetic done ONCE per sample, corner pixel indices + attention-scaled bilinear weights
 //     staged in shared memory (32 B per sample);
@@ -16,14 +17,18 @@
 //     (fp32) or 64-byte (bf16) contiguous row per pair, 4 corners x 4 points in flight per lane;
 //     fp32 accumulation in registers, one 16-byte store per lane.
 // No tensor cores: the op is a gather, not a contraction.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rdetr {
 
-constexpr int kFwdThreads = 256;
-
-template <typename VT, int CH, int D, typename IO>
-__global__ void __launch_bounds__(kFwdThreads)
+// THREADS: CTA size.  Small CTAs win: the kernel is latency bound (ncu: long-scoreboard stalls dominate, the
+// L1 data pipe is 61 % busy), and with 64 threads the prologue / barrier of one CTA overlaps the gathers
+// of the others resident on the SM (tools/tune_fwd.py: 0.68 -> 0.61 ms at configs[1]; capping fp32 at 32
+// registers for full occupancy gives 0.57 ms).  MINB = 0 leaves the register budget to ptxas.
+template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
 msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, VT *__restrict__ out, int S, int M, int L, int Nq,
                 int P, long long total_pairs)
@@ -31,6 +36,7 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
     constexpr int kLanes = D / kCh;
+    constexpr int kFwdThreads = THREADS;
     constexpr int kPairs = kFwdThreads / kLanes;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -141,16 +147,16 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     SL::store(out + gp * D + lane * kCh, acc);
 }
 
-template <typename VT, int CH, typename IO>
-static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S,
-                      int M, int L, int Nq, int P, cudaStream_t stream)
+template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
+static int launch_fwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B,
+                              int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
-    constexpr int kPairs = kFwdThreads / kLanes;
+    constexpr int kPairs = THREADS / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
-    auto kern = msda_fwd_kernel<VT, CH, D, IO>;
+    auto kern = msda_fwd_kernel<VT, CH, D, IO, THREADS, MINB>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_fwd)"))
@@ -158,9 +164,35 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
     }
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_forward: B*Nq*M too large (%lld pairs)", total_pairs);
-    kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io, static_cast<VT *>(out),
-                                                        S, M, L, Nq, P, total_pairs);
+    kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io, static_cast<VT *>(out), S, M,
+                                                    L, Nq, P, total_pairs);
     return check_cuda(cudaGetLastError(), "msda_fwd_kernel launch");
+}
+
+template <typename VT, int CH, typename IO>
+static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S,
+                      int M, int L, int Nq, int P, cudaStream_t stream)
+{
+#ifdef RDETR_TUNE_FWD
+    // tuning builds only (tools/tune_fwd.py): CTA size from the environment
+    const char *e = getenv("RDETR_MSDA_FWD_VARIANT");
+    const int v = e ? atoi(e) : 0;
+    if (v == 1) return launch_fwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 2) return launch_fwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 3) return launch_fwd_variant<VT, CH, IO, 32>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 4) return launch_fwd_variant<VT, CH, IO, 64, 0>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 5) return launch_fwd_variant<VT, CH, IO, 64, 24>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 6) return launch_fwd_variant<VT, CH, IO, 128, 16>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 7) return launch_fwd_variant<VT, CH, IO, 32, 32>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+#endif
+    // fp32: cap at 32 registers (32 CTAs x 2 warps = full occupancy; 0.62 -> 0.57 ms at configs[1]) as long as
+    // one image's value tensor fits L2 comfortably; for the 1200x2000 pyramid (209 MB per image) the extra
+    // CTAs in flight only widen the window of lines competing for L2 (0.90 ms uncapped vs 1.15 ms capped).
+    // The bf16 lanes hold 8 channels and spill under the cap, so they keep ptxas' own choice (71 registers).
+    const bool fits_l2 = (size_t)S * M * 32 * sizeof(VT) <= (size_t)96 << 20;
+    if (sizeof(VT) == 4 && fits_l2)
+        return launch_fwd_variant<VT, CH, IO, 64, sizeof(VT) == 4 ? 32 : 0>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    return launch_fwd_variant<VT, CH, IO, 64, 0>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
 }
 
 int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype)

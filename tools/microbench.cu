@@ -31,6 +31,52 @@ __global__ void gather_rows(const uint4* __restrict__ table, uint32_t nrows, uin
     if (acc == 123.456f) sink[0] = acc;
 }
 
+// rows gathered with narrower per-lane loads: W words (4 bytes each) per lane, 32/W lanes per 128-byte row
+template <int W>
+__global__ void gather_rows_narrow(const float* __restrict__ table, uint32_t nrows, int iters, float* sink)
+{
+    constexpr int LANES = 32 / W;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t group = tid / LANES, lane = tid % LANES;
+    float acc = 0.f;
+    uint32_t seed = group * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        float v[8][W];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            seed = hash32(seed + u);
+            const float* p = table + (size_t)(seed % nrows) * 32 + lane * W;
+            if (W == 1) v[u][0] = __ldg(p);
+            else { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); v[u][0] = t.x; v[u][W - 1] = t.y; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u][0] + v[u][W - 1];
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
+// cheap index arithmetic (LCG + mask, nrows a power of two) so that the load path, not the ALU, is the limit;
+// INFLIGHT independent 16-byte loads per lane before any use
+template <int INFLIGHT>
+__global__ void gather_rows_lean(const uint4* __restrict__ table, uint32_t row_mask, int iters, float* sink)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t group = tid >> 3, lane = tid & 7;
+    float acc = 0.f;
+    uint32_t seed = group * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        uint4 v[INFLIGHT];
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) {
+            seed = seed * 1664525u + 1013904223u;
+            v[u] = __ldg(table + (size_t)((seed >> 9) & row_mask) * 8 + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; ++u) acc += __uint_as_float(v[u].x);
+    }
+    if (acc == 123.456f) sink[0] = acc;
+}
+
 // same access pattern but "spatially coherent": consecutive groups read rows near group index (L1 reuse)
 template <int LANES>
 __global__ void gather_rows_local(const uint4* __restrict__ table, uint32_t nrows, uint32_t row_stride16, int iters, float* sink)
@@ -231,6 +277,27 @@ int main()
         ms = time_ms([&] { gather_rows<4><<<blocks, threads>>>(table, c.rows, c.stride16, iters, sink); });
         rows = nthreads / 4 * iters * 8;
         printf("gather  64B rows (4 lanes x 16B) random %-12s : %8.3f ms  %7.2f Grows/s  %7.2f TB/s\n", c.name, ms, rows / ms / 1e6, rows * 64 / ms / 1e9);
+    }
+    for (uint32_t lg : {15u, 20u}) {
+        const uint32_t mask = (1u << lg) - 1;
+        for (int ctas_per_sm : {2, 4, 8}) {
+            const int blk = SMS * ctas_per_sm;
+            float ms = time_ms([&] { gather_rows_lean<8><<<blk, 256>>>(table, mask, 256 / ctas_per_sm, sink); });
+            double rows = (double)blk * 256 / 8 * (256 / ctas_per_sm) * 8;
+            printf("lean gather 128B rows, 2^%u rows, %d CTAs/SM x 256 thr,  8 in flight : %8.3f ms  %7.2f Grows/s\n", lg, ctas_per_sm, ms, rows / ms / 1e6);
+            ms = time_ms([&] { gather_rows_lean<16><<<blk, 256>>>(table, mask, 128 / ctas_per_sm, sink); });
+            rows = (double)blk * 256 / 8 * (128 / ctas_per_sm) * 16;
+            printf("lean gather 128B rows, 2^%u rows, %d CTAs/SM x 256 thr, 16 in flight : %8.3f ms  %7.2f Grows/s\n", lg, ctas_per_sm, ms, rows / ms / 1e6);
+        }
+    }
+    for (auto& c : cfgs) {
+        const float* ft = reinterpret_cast<const float*>(table);
+        float ms = time_ms([&] { gather_rows_narrow<1><<<blocks, threads>>>(ft, c.rows, iters, sink); });
+        double rows = nthreads / 32 * iters * 8;
+        printf("gather 128B rows (32 lanes x 4B, 1 row/instr) %-12s : %8.3f ms  %7.2f Grows/s\n", c.name, ms, rows / ms / 1e6);
+        ms = time_ms([&] { gather_rows_narrow<2><<<blocks, threads>>>(ft, c.rows, iters, sink); });
+        rows = nthreads / 16 * iters * 8;
+        printf("gather 128B rows (16 lanes x 8B, 2 rows/instr) %-12s : %8.3f ms  %7.2f Grows/s\n", c.name, ms, rows / ms / 1e6);
     }
     {
         float ms = time_ms([&] { gather_rows_local<8><<<blocks, threads>>>(table, 22323u * 8, 8, iters, sink); });
