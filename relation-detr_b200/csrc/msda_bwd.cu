@@ -28,8 +28,8 @@ namespace rdetr {
 
 int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype);
 
-template <typename VT, int CH, int D, typename IO, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
                 float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs)
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
     reinterpret_cast<uint4 *>(dst)[i] = t;
 }
 
-template <typename VT, int CH, typename IO, int THREADS>
+template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
 static int launch_bwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
                               float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
@@ -246,7 +246,7 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
     constexpr int kPairs = THREADS / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
-    auto kern = msda_bwd_kernel<VT, CH, D, IO, THREADS>;
+    auto kern = msda_bwd_kernel<VT, CH, D, IO, THREADS, MINB>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_bwd)"))
@@ -268,8 +268,10 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
     const int v = e ? atoi(e) : 0;
     if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
     if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
 #endif
-    // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls
+    // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls; register
+    // caps for more occupancy spill and are 30-70 % slower (variant 3)
     return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
 }
 

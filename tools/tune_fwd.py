@@ -2,7 +2,7 @@
 
 Build: nvcc ... -DRDETR_TUNE_FWD -o tools/librdetr_tune.so relation-detr_b200/csrc/*.cu; variant 0 = shipped default
 (forward 64 threads with fp32 capped at 32 registers, backward 128 threads); forward 1/2/3 = 256/128/32 threads,
-4 = 64 threads uncapped, 5/6/7 = (64 thr, 24 CTAs), (128, 16), (32, 32); backward 1/2 = 256/64 threads."""
+4 = 64 threads uncapped, 5/6/7 = (64 thr, 24 CTAs), (128, 16), (32, 32); backward 1/2 = 256/64 threads, 3 = 128 threads capped at 40 registers."""
 import os
 import subprocess
 import sys
@@ -53,7 +53,7 @@ for v in (0, 1, 2, 3, 4, 5, 6, 7):
     env = dict(os.environ, RDETR_MSDA_FWD_VARIANT=str(v), RDETR_OPS_LIB=lib)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
-for v in (0, 1, 2):
+for v in (0, 1, 2, 3):
     env = dict(os.environ, RDETR_MSDA_BWD_VARIANT=str(v), RDETR_OPS_LIB=lib)
     out = subprocess.run([sys.executable, "-c", code_bwd], env=env, capture_output=True, text=True)
     print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:])
