@@ -35,7 +35,7 @@ METRIC = "MSDeformAttn fwd+bwd GB/s"
 UNIT = "GB/s"
 WORKLOAD = "msda_enc_800x1333_b8"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-NCU_BWD_DRAM_BYTES = 1_279_300_000  # 849.7 MB read + 429.6 MB written (profiles/r01a_ncu_summary.md), vs 1 097.2 MB algorithmic
+NCU_BWD_DRAM_BYTES = 1_287_700_000  # 851.5 MB read + 436.3 MB written (profiles/r01d_ncu_summary.md), vs 1 097.2 MB algorithmic
 
 
 def measured_peak():
@@ -354,7 +354,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "msda_bwd_kernel<float,32> (+ grad_value zero-fill memset, both inside rdetr_msda_backward)",
                          "achieved": round(bwd_b / bwd_max / 1e6, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(bwd_b / bwd_max / 1e6 / peak, 4), "traffic": NCU_BWD_DRAM_BYTES if args.loc == "S" else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of msda_bwd_kernel per launch, ncu --set full, profiles/r01a_ncu_summary.md (loc S)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of msda_bwd_kernel per launch, ncu --set full, profiles/r01d_ncu_summary.md (loc S)",
                          "algorithmic_bytes": bwd_b, "peak_source": peak_src,
                          "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
                          "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4),
