@@ -410,6 +410,13 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();  // tile `buf` (and, on the first pass, s_row) visible to every warp
+        // apply the ReLU mask once per CTA (warp w owns head w of the tile) instead of once per consumer warp
+#pragma unroll 4
+        for (int r = 0; r < kBwdTileRows; ++r) {
+            const float raw = s_g[buf][r][w][lane];
+            s_g[buf][r][w][lane] = ((s_bits[buf][r][w] >> lane) & 1u) ? raw : 0.f;
+        }
+        __syncthreads();
 
         // two rows per iteration: two independent feature chains in flight per lane (the kernel is
         // latency bound at 2 CTAs/SM otherwise); rows past `trows` read zeroed s_g / padded s_row
@@ -442,11 +449,10 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
             }
 #pragma unroll
             for (int h = 0; h < kRelHeads; ++h) {
-                const float g0 = ((s_bits[buf][r][h] >> lane) & 1u) ? s_g[buf][r][h][lane] : 0.f;
-                const float g1 = ((s_bits[buf][r + 1][h] >> lane) & 1u) ? s_g[buf][r + 1][h][lane] : 0.f;
+                const float g0 = s_g[buf][r][h][lane], g1 = s_g[buf][r + 1][h][lane];
 #pragma unroll
                 for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g1, f[1][n], fmaf(g0, f[0][n], acc[h][n]));
-                accb[h] += g0 + g1;
+                if (w == 0) accb[h] += g0 + g1;  // grad_bias is accumulated by one warp only (warp-uniform branch)
             }
         }
         __syncthreads();  // every warp is done with tile `buf` before the copy after next overwrites it
