@@ -66,28 +66,37 @@ rel_tables_kernel(const float *__restrict__ boxes, const float *__restrict__ dim
     row[28 + k] = (float)c;
 }
 
-// sin/cos of q = es / d for the centre features
+// sin/cos of theta = es / d for the centre features.
+// EXACT: IEEE division + accurate sincosf, as torch evaluates it.
+// FAST: the angle is never materialised in fp32 (theta reaches ~1e3 rad, ulp 6e-5).  With c = 1/(2 pi d)
+// split into chi + clo, t = es*chi is the angle in revolutions; n = rint(t); the fractional part
+// f = fma(es, chi, -n) + es*clo is exact to one rounding at |f| <= 0.5, and sin/cos(2 pi f) go to MUFU.
 template <bool FAST>
-__device__ __forceinline__ void angle_sincos(float es, float d, float inv_d, float &sn, float &cs)
+__device__ __forceinline__ void angle_sincos(float es, float d_or_chi, float invd_or_clo, float &sn, float &cs)
 {
     if constexpr (!FAST) {
-        const float th = es / d;  // IEEE division: nvcc emits div.rn.f32 without -use_fast_math
+        const float th = es / d_or_chi;  // IEEE division: nvcc emits div.rn.f32 without -use_fast_math
         sincosf(th, &sn, &cs);
     } else {
-        // correctly rounded quotient in all but pathological cases: q + fma residual * 1/d
-        float q = es * inv_d;
-        const float r = fmaf(-q, d, es);
-        q = fmaf(r, inv_d, q);
-        // Cody-Waite: x = q - n*2pi with 2pi = hi + lo, hi = 6.282958984375 (15 significant bits).
-        // |q| <= ~1.2e3 here (|e| <= log(1/eps + 1) = 11.5, scale 100), so n < 2^8 and n*hi is exact;
-        // the neglected third term is 4.3e-12 * n.
-        const float n = rintf(q * 0.15915494309189535f);
-        float x = fmaf(n, -6.282958984375f, q);
-        x = fmaf(n, -2.2632280888501555e-4f, x);
+        const float n = rintf(es * d_or_chi);
+        float f = fmaf(es, d_or_chi, -n);
+        f = fmaf(es, invd_or_clo, f);
+        const float x = f * 6.283185307179586f;
         sn = __sinf(x);
         cs = __cosf(x);
     }
 }
+
+// hi/lo split of 1 / (2 pi d) for the FAST angle evaluation
+__device__ __forceinline__ void rev_constants(float d, float &chi, float &clo)
+{
+    const double c = 1.0 / (6.283185307179586476925 * (double)d);
+    chi = (float)c;
+    clo = (float)(c - (double)chi);
+}
+
+// (A MUFU.LG2-based log was measured too: 3 % faster, but it adds ~5e-6 of error at the k = 0 frequency and
+// costs FAST its accuracy advantage over the reference's own fp32 evaluation, so logf stays accurate.)
 
 // Packed fp32 pairs (Blackwell fma.rn.f32x2): one issue slot performs two IEEE FMAs.  The forward is
 // issue bound (ncu: 73 % issue-active, 50 % FMA pipe), so halving the instruction count of the
@@ -178,8 +187,8 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
     }
     if (tid < kRelHeads) s_bias[tid] = bias[tid];
     if (tid < kRelK) {
-        s_d[tid] = dim_t[tid];
-        s_invd[tid] = 1.0f / dim_t[tid];
+        if constexpr (FAST) rev_constants(dim_t[tid], s_d[tid], s_invd[tid]);  // (chi, clo) of 1/(2 pi d_k)
+        else { s_d[tid] = dim_t[tid]; s_invd[tid] = 1.0f / dim_t[tid]; }
     }
     {
         const float *rows = (FAST ? src_tab : src) + ((size_t)b * N1 + i_cta) * kRowF;
@@ -228,7 +237,7 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
             for (int r = 0; r < R; ++r) {
                 const float *row = s_row[lrow + r];
                 float e;
-                if constexpr (FAST) e = logf(fabsf(row[c] - t_xy) * row[2 + c] + 1.0f);
+                if constexpr (FAST) e = logf(fmaf(fabsf(row[c] - t_xy), row[2 + c], 1.0f));
                 else e = logf(fabsf(row[c] - t_xy) / (row[2 + c] + eps) + 1.0f);
                 es[r] = e * scale;  // (x * scale) first, position_encoding.py:133
             }
@@ -244,17 +253,28 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
             if constexpr (FAST) {
-#pragma unroll 2
-                for (int k = 0; k < kRelK; ++k) {
-                    const float sBk = s_tgt[4 + c * 8 + k][lane], cBk = s_tgt[20 + c * 8 + k][lane];
-                    float sn[R], cs[R];
+#pragma unroll 1
+                for (int k4 = 0; k4 < kRelK; k4 += 4) {
+                    float4 sA4[R], cA4[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        const float sA = s_row[lrow + r][4 + c * 8 + k], cA = s_row[lrow + r][20 + c * 8 + k];
-                        sn[r] = fmaf(sA, cBk, -(cA * sBk));  // sin(A - B)
-                        cs[r] = fmaf(cA, cBk, sA * sBk);     // cos(A - B)
+                        sA4[r] = *reinterpret_cast<const float4 *>(&s_row[lrow + r][4 + c * 8 + k4]);
+                        cA4[r] = *reinterpret_cast<const float4 *>(&s_row[lrow + r][20 + c * 8 + k4]);
                     }
-                    project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const int k = k4 + kk;
+                        const float sBk = s_tgt[4 + c * 8 + k][lane], cBk = s_tgt[20 + c * 8 + k][lane];
+                        float sn[R], cs[R];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const float sA = kk == 0 ? sA4[r].x : kk == 1 ? sA4[r].y : kk == 2 ? sA4[r].z : sA4[r].w;
+                            const float cA = kk == 0 ? cA4[r].x : kk == 1 ? cA4[r].y : kk == 2 ? cA4[r].z : cA4[r].w;
+                            sn[r] = fmaf(sA, cBk, -(cA * sBk));  // sin(A - B)
+                            cs[r] = fmaf(cA, cBk, sA * sBk);     // cos(A - B)
+                        }
+                        project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+                    }
                 }
             } else {
                 const float t_den = c == 0 ? w2e : h2e;
@@ -340,11 +360,11 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
         for (int idx = tid; idx < kBwdRowsPerCta * kRowF; idx += 32 * kRelBwdWarps) flat[idx] = idx < nrows * kRowF ? rows[idx] : 1.0f;
     }
 
-    float d[4], invd[4];
+    float d[4], invd[4];  // EXACT: (d_k, 1/d_k); FAST: (chi, clo) of 1/(2 pi d_k)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        d[k] = __ldg(dim_t + k0 + k);
-        invd[k] = 1.0f / d[k];
+        if constexpr (FAST) rev_constants(__ldg(dim_t + k0 + k), d[k], invd[k]);
+        else { d[k] = __ldg(dim_t + k0 + k); invd[k] = 1.0f / d[k]; }
     }
     // per-column constants of this warp's feature
     float t_xy = 0.f, t_den = 1.f;  // centre coordinate / (size + eps) of the tgt box for feature c
@@ -427,7 +447,7 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                 const float *row = s_row[t0 + r + u];
                 if constexpr (FAST) {
                     if (c < 2) {
-                        const float es = logf(fabsf(row[c] - t_xy) * row[2 + c] + 1.0f) * scale;
+                        const float es = logf(fmaf(fabsf(row[c] - t_xy), row[2 + c], 1.0f)) * scale;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) angle_sincos<true>(es, d[k], invd[k], f[u][2 * k], f[u][2 * k + 1]);
                     } else {

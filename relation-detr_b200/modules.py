@@ -136,7 +136,7 @@ class PositionRelationEmbedding(nn.Module):
         self.temperature = temperature
         self.scale = scale
         self.eps = 1e-5  # box_rel_encoding default (relation_transformer.py:481)
-        # RDETR_REL_FAST by default: measured against the fp64 truth at N=900 it is closer (max 8.6e-6 / mean
+        # RDETR_REL_FAST by default: measured against the fp64 truth at N=900 it is closer (max 9.1e-6 / mean
         # 3.4e-7) than the reference's own fp32 evaluation (1.3e-5 / 4.5e-7; 4.5e-4 with torch's default
         # TF32 conv) -- profiles/r01_rel_accuracy.json.  False selects the operation-for-operation EXACT mode.
         self.fast_math = True
