@@ -185,6 +185,36 @@ def time_msda(torch, ops, inp, steps, warmup, dtype):
     return total, fwd, bwd
 
 
+def time_msda_fused(torch, ops, wl, shape, steps, warmup, dtype, with_mask=True):
+    """Same shape through rdetr::msda_fused_forward/backward (softmax, location arithmetic and padding mask
+    inside the kernels): raw offsets / logits / reference points in, as the drop-in module calls it."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(0)
+    B, S, Nq, M, L, P = shape.batch, shape.S, shape.Nq, shape.heads, shape.L, shape.points
+    ss, lsi = wl.shape_tensors(shape.levels, dev)
+    value = torch.randn((B, S, M, 32), device=dev, generator=g).to(dtype)
+    off = (wl.grid_init(M, L, P).to(dev)[None, None] + torch.randn((B, Nq, M, L, P, 2), device=dev, generator=g)).to(dtype)
+    logits = torch.randn((B, Nq, M, L * P), device=dev, generator=g).to(dtype)
+    ref = wl.full_reference_points(shape.levels, dev)[None, :, None, :].expand(B, -1, L, -1).contiguous()
+    mask = torch.zeros((B, S), dtype=torch.bool, device=dev) if with_mask else None
+    go = torch.randn((B, Nq, M * 32), device=dev, generator=g).to(dtype)
+    for _ in range(warmup):
+        ops.msda_fused_forward(value, ss, lsi, ref, off, logits, mask)
+        ops.msda_fused_backward(value, ss, lsi, ref, off, logits, mask, go)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    torch.cuda.synchronize()
+    for i in range(steps):
+        ev[i][0].record()
+        ops.msda_fused_forward(value, ss, lsi, ref, off, logits, mask)
+        ev[i][1].record()
+        ops.msda_fused_backward(value, ss, lsi, ref, off, logits, mask, go)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    return {"fwd_ms": round(fwd, 4), "bwd_ms": round(bwd, 4), "ms": round(fwd + bwd, 4)}
+
+
 def time_e2e(torch, rd, inp, steps, warmup):
     """Public host-buffer API (relation_detr_b200.hostpipe.MsdaHostPipeline ->
     MultiScaleDeformableAttnFunction.apply + autograd): every step copies value/loc/attn/grad_out from
@@ -329,6 +359,10 @@ def run_ours(args):
             t, f, b = time_msda(torch, ops, data, k, w, torch.bfloat16)
             extra[f"msda_enc_b8_bf16_loc{kind}"] = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((f16 + b16) / t / 1e6, 1)}
         del inp_o
+        extra["msda_enc_b8_f32_fused_prologue"] = time_msda_fused(torch, ops, workloads, shape, k, w, torch.float32)
+        extra["msda_enc_b8_bf16_fused_prologue"] = time_msda_fused(torch, ops, workloads, shape, k, w, torch.bfloat16)
+        extra["msda_enc_b8_f32_fused_prologue_nomask"] = time_msda_fused(torch, ops, workloads, shape, k, w, torch.float32, False)
+        extra["msda_enc_b8_bf16_fused_prologue_nomask"] = time_msda_fused(torch, ops, workloads, shape, k, w, torch.bfloat16, False)
         for name, kind in (("msda_dec_900_b8", "D"), ("msda_dec_1500_b8", "D"), ("msda_enc_1200x2000_b1", "S")):
             s2 = workloads.MSDA_SHAPES[name]
             d2 = workloads.make_msda_inputs(s2, kind, seed=0, device=dev)

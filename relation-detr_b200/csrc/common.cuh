@@ -223,16 +223,35 @@ struct FusedIO {
     int ref_dim;             // 2 or 4
 };
 
+// streaming loads of the fused prologue's inputs (read once; keep them out of L1 like loc / attn)
+__device__ __forceinline__ float ld_stream_scalar(const float *p) { return ld_stream_f1(p); }
+__device__ __forceinline__ float ld_stream_scalar(const __nv_bfloat16 *p)
+{
+    unsigned short r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return __uint_as_float((uint32_t)r << 16);
+}
+__device__ __forceinline__ float2 ld_stream_pair(const float *p) { return ld_stream_f2(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float2 ld_stream_pair(const __nv_bfloat16 *p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return make_float2(bf16lo(r), bf16hi(r));
+}
+
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ void from_f32(float &d, float v) { d = v; }
 __device__ __forceinline__ void from_f32(__nv_bfloat16 &d, float v) { d = __float2bfloat16_rn(v); }
 
-// sampling location of one sample from reference point + raw offset, evaluated in torch's order
-__device__ __forceinline__ float2 fused_location(const float *rp, int ref_dim, float offx, float offy, int W, int H, int P)
+// sampling location of one sample from reference point + raw offset.  torch divides (off / W, off / P); the
+// kernel multiplies by the reciprocal (exact for the power-of-two P of every shipped config, <= 1 ulp of the
+// offset term otherwise -- the same class of difference as the summation order of the softmax).
+__device__ __forceinline__ float2 fused_location(const float *rp, int ref_dim, float offx, float offy, float invW, float invH,
+                                                 float invP)
 {
-    if (ref_dim == 2) return make_float2(rp[0] + offx / (float)W, rp[1] + offy / (float)H);
-    return make_float2(rp[0] + ((offx / (float)P) * rp[2]) * 0.5f, rp[1] + ((offy / (float)P) * rp[3]) * 0.5f);
+    if (ref_dim == 2) return make_float2(fmaf(offx, invW, rp[0]), fmaf(offy, invH, rp[1]));
+    return make_float2(fmaf((offx * invP) * rp[2], 0.5f, rp[0]), fmaf((offy * invP) * rp[3], 0.5f, rp[1]));
 }
 
 #endif  // __CUDACC__

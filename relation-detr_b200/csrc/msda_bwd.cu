@@ -42,6 +42,10 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
+    __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
+    __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
+    __shared__ int s_b[THREADS / (D / CH)];
+    const float inv_P = 1.0f / (float)P;
 
     const int LP = L * P;
     const int stride = LP + 1;
@@ -52,6 +56,8 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_H[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x];
         s_W[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x + 1];
         s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
+        s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
+        s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
     }
     __syncthreads();
 
@@ -63,17 +69,29 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     // ---- phase 1 -----------------------------------------------------------------------------------
     float2 *s_stat = reinterpret_cast<float2 *>(s_meta + kPairs * stride);  // FusedIO: per-pair softmax statistics
     if constexpr (IO::kFused) {
-        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
-            const int pair = s / LP;
-            s_meta[pair * stride + (s - pair * LP)].x = to_f32(io.logits[pair0 * LP + s]);
-        }
-        __syncthreads();
-        if (threadIdx.x < npairs) {
-            const float4 *row = s_meta + threadIdx.x * stride;
-            float mx = -INFINITY, sum = 0.f;
-            for (int lp = 0; lp < LP; ++lp) mx = fmaxf(mx, row[lp].x);
-            for (int lp = 0; lp < LP; ++lp) sum += expf(row[lp].x - mx);
-            s_stat[threadIdx.x] = make_float2(mx, sum);
+        // softmax statistics per pair: kLanes lanes split the L*P logits, xor-shuffle reduction (see msda_fwd.cu)
+        const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
+        const auto *zrow = io.logits + (pair0 + (spair < npairs ? spair : 0)) * LP;
+        float4 *zslot = s_meta + (spair < npairs ? spair : 0) * stride;  // .x of every slot keeps the logit for the main loop
+        float mx = -INFINITY;
+        if (spair < npairs)
+            for (int lp = slane; lp < LP; lp += kLanes) {
+                const float z = ld_stream_scalar(zrow + lp);
+                zslot[lp].x = z;
+                mx = fmaxf(mx, z);
+            }
+#pragma unroll
+        for (int off = kLanes / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.f;
+        if (spair < npairs)
+            for (int lp = slane; lp < LP; lp += kLanes) sum += __expf(zslot[lp].x - mx);
+#pragma unroll
+        for (int off = kLanes / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (slane == 0 && spair < npairs) {
+            s_stat[spair] = make_float2(mx, sum);
+            const long long bq_ = (pair0 + spair) / M;
+            s_bq[spair] = bq_;
+            s_b[spair] = (int)(bq_ / Nq);
         }
         __syncthreads();
     }
@@ -86,11 +104,11 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         long long bq = 0;
         if constexpr (IO::kFused) {
             const float2 st = s_stat[pair];
-            a = expf(s_meta[pair * stride + lp].x - st.x) / st.y;
-            bq = (pair0 + pair) / M;
+            a = __expf(s_meta[pair * stride + lp].x - st.x) / st.y;
+            bq = s_bq[pair];
             const long long gs = pair0 * LP + s;
-            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, to_f32(io.offsets[2 * gs]),
-                                to_f32(io.offsets[2 * gs + 1]), s_W[l], s_H[l], P);
+            const float2 off = ld_stream_pair(io.offsets + 2 * gs);
+            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, off.x, off.y, s_invW[l], s_invH[l], inv_P);
         } else {
             xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
             a = ld_stream_f1(io.attn + pair0 * LP + s);
@@ -98,7 +116,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
         if constexpr (IO::kFused) {
             if (io.mask != nullptr) {
-                const uint8_t *mrow = io.mask + (bq / Nq) * (long long)S;
+                const uint8_t *mrow = io.mask + (long long)s_b[pair] * S;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;
@@ -182,11 +200,15 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     // ---- phase 3: dense stores of the per-sample gradients -------------------------------------------
     if constexpr (IO::kFused) {
         // softmax backward needs sum_j a_j * dL/da_j of the pair; then chain through the location formula
-        if (threadIdx.x < npairs) {
-            const float4 *row = s_meta + threadIdx.x * stride;
+        {
+            const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
+            const float4 *row = s_meta + (spair < npairs ? spair : 0) * stride;
             float dot = 0.f;
-            for (int lp = 0; lp < LP; ++lp) dot = fmaf(row[lp].w, row[lp].z, dot);
-            s_stat[threadIdx.x].x = dot;
+            if (spair < npairs)
+                for (int lp = slane; lp < LP; lp += kLanes) dot = fmaf(row[lp].w, row[lp].z, dot);
+#pragma unroll
+            for (int off = kLanes / 2; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+            if (slane == 0 && spair < npairs) s_stat[spair].x = dot;
         }
         __syncthreads();
         for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
@@ -201,7 +223,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 gox = glx / (float)s_W[l];
                 goy = gly / (float)s_H[l];
             } else {
-                const float *rp = io.ref + (((pair0 + pr) / M) * L + l) * 4;
+                const float *rp = io.ref + (s_bq[pr] * L + l) * 4;
                 gox = ((glx * 0.5f) * rp[2]) / (float)P;
                 goy = ((gly * 0.5f) * rp[3]) / (float)P;
             }

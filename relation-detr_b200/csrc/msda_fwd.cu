@@ -41,6 +41,10 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
+    __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
+    __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
+    __shared__ int s_b[THREADS / (D / CH)];
+    const float inv_P = 1.0f / (float)P;
 
     const int LP = L * P;
     const int stride = LP + 1;  // one slot of padding de-phases consecutive pairs across banks
@@ -51,6 +55,8 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_H[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x];
         s_W[threadIdx.x] = (int)spatial_shapes[2 * threadIdx.x + 1];
         s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
+        s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
+        s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
     }
     __syncthreads();
 
@@ -62,17 +68,30 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     const int nsamples = npairs * LP;
     float2 *s_stat = reinterpret_cast<float2 *>(s_wgt + kPairs * stride);  // FusedIO: per-pair (max, sum) of the softmax
     if constexpr (IO::kFused) {
-        for (int s = threadIdx.x; s < nsamples; s += kFwdThreads) {
-            const int pair = s / LP;
-            s_wgt[pair * stride + (s - pair * LP)].x = to_f32(io.logits[pair0 * LP + s]);
-        }
-        __syncthreads();
-        if (threadIdx.x < npairs) {
-            const float4 *row = s_wgt + threadIdx.x * stride;
-            float mx = -INFINITY, sum = 0.f;
-            for (int lp = 0; lp < LP; ++lp) mx = fmaxf(mx, row[lp].x);
-            for (int lp = 0; lp < LP; ++lp) sum += expf(row[lp].x - mx);
-            s_stat[threadIdx.x] = make_float2(mx, sum);
+        // softmax statistics of every pair: its kLanes lanes (the same lanes that gather for it in phase 2)
+        // split the L*P logits and combine with xor-shuffles -- no shared-memory staging, one barrier
+        const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
+        const auto *zrow = io.logits + (pair0 + (spair < npairs ? spair : 0)) * LP;
+        float4 *zslot = s_wgt + (spair < npairs ? spair : 0) * stride;  // .x of every slot keeps the logit for the main loop
+        float mx = -INFINITY;
+        if (spair < npairs)
+            for (int lp = slane; lp < LP; lp += kLanes) {
+                const float z = ld_stream_scalar(zrow + lp);
+                zslot[lp].x = z;
+                mx = fmaxf(mx, z);
+            }
+#pragma unroll
+        for (int off = kLanes / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        float sum = 0.f;
+        if (spair < npairs)
+            for (int lp = slane; lp < LP; lp += kLanes) sum += __expf(zslot[lp].x - mx);
+#pragma unroll
+        for (int off = kLanes / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (slane == 0 && spair < npairs) {
+            s_stat[spair] = make_float2(mx, sum);
+            const long long bq_ = (pair0 + spair) / M;
+            s_bq[spair] = bq_;
+            s_b[spair] = (int)(bq_ / Nq);
         }
         __syncthreads();
     }
@@ -85,11 +104,11 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         long long bq = 0;
         if constexpr (IO::kFused) {
             const float2 st = s_stat[pair];
-            a = expf(s_wgt[pair * stride + lp].x - st.x) / st.y;  // softmax as torch evaluates it
-            bq = (pair0 + pair) / M;
+            a = __expf(s_wgt[pair * stride + lp].x - st.x) / st.y;  // exp(z - max) / sum, MUFU exp (2 ulp)
+            bq = s_bq[pair];
             const long long gs = pair0 * LP + s;
-            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, to_f32(io.offsets[2 * gs]),
-                                to_f32(io.offsets[2 * gs + 1]), s_W[l], s_H[l], P);
+            const float2 off = ld_stream_pair(io.offsets + 2 * gs);
+            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, off.x, off.y, s_invW[l], s_invH[l], inv_P);
         } else {
             xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
             a = ld_stream_f1(io.attn + pair0 * LP + s);
@@ -97,7 +116,7 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
         if constexpr (IO::kFused) {
             if (io.mask != nullptr) {  // padded pixels read as zero (value.masked_fill of the reference, :318-319)
-                const uint8_t *mrow = io.mask + (bq / Nq) * (long long)S;
+                const uint8_t *mrow = io.mask + (long long)s_b[pair] * S;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;

@@ -17,6 +17,7 @@ ap.add_argument("--loc", default="S")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--shape", default="msda_enc_800x1333_b8")
+ap.add_argument("--fused", action="store_true", help="run the fused-prologue kernels instead of the plain ones")
 a = ap.parse_args()
 dev = "cuda:0"
 if a.what in ("msda", "all"):
@@ -24,6 +25,18 @@ if a.what in ("msda", "all"):
     inp = workloads.make_msda_inputs(shape, a.loc, seed=0, device=dev)
     dt = torch.float32 if a.dtype == "f32" else torch.bfloat16
     v, go = inp["value"].to(dt), inp["grad_output"].to(dt)
+    if a.fused:
+        g = torch.Generator(device=dev).manual_seed(0)
+        B, S, Nq, M, L, P = shape.batch, shape.S, shape.Nq, shape.heads, shape.L, shape.points
+        off = (workloads.grid_init(M, L, P).to(dev)[None, None] + torch.randn((B, Nq, M, L, P, 2), device=dev, generator=g)).to(dt)
+        logits = torch.randn((B, Nq, M, L * P), device=dev, generator=g).to(dt)
+        ref = workloads.full_reference_points(shape.levels, dev)[None, :, None, :].expand(B, -1, L, -1).contiguous()
+        for _ in range(a.iters):
+            ops.msda_fused_forward(v, inp["spatial_shapes"], inp["level_start_index"], ref, off, logits, None)
+            ops.msda_fused_backward(v, inp["spatial_shapes"], inp["level_start_index"], ref, off, logits, None, go)
+        torch.cuda.synchronize()
+        print("profile_ops done")
+        sys.exit(0)
     for _ in range(a.iters):
         out = ops.msda_forward(v, inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"])
         ops.msda_backward(v, inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"], go)
