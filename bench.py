@@ -137,6 +137,31 @@ def time_cpu_port(steps: int, warmup: int, sample_batch: int = 1, loc_kind: str 
     return (fwd + bwd) / dt / 1e9, dt * 1e3, cores, f"batch {sample_batch} of {WORKLOAD} ({sample_batch}/{full.batch} of one step), loc {loc_kind}, fp32, {steps} timed passes"
 
 
+def time_cpu_rel(steps: int = 3, batch: int = 2, n: int = 900):
+    """The reference's eager relation embedding (oracle/torch_port.py, fwd + autograd bwd) on the host cores, as a
+    second CPU baseline next to the MSDA one (BASELINE.json configs[2], bounded sample: `batch` of 8 images)."""
+    import torch
+    from oracle import torch_port
+    from relation_detr_b200 import workloads
+
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    r = workloads.make_rel_inputs(workloads.RelShape("cpu", batch, n, n), seed=0)
+
+    def step():
+        w = r["weight"].detach().requires_grad_(True)
+        b = r["bias"].detach().requires_grad_(True)
+        torch_port.rel_eager(r["src_boxes"], r["tgt_boxes"], w, b).backward(r["grad_output"])
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    nbytes = 2 * batch * 8 * n * n * 4
+    return {"value": round(nbytes / dt / 1e9, 4), "unit": UNIT, "ms_per_sample": round(dt * 1e3, 2), "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"relation embedding fwd+bwd, B={batch} (of 8), N={n}, fp32, {steps} timed passes"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -375,7 +400,8 @@ def run_ours(args):
             extra[name + "_fast"] = time_rel(torch, ops, workloads, name, k, w, True)
     if rank == 0 and not args.no_cpu_baseline:
         gbs, cms, cores, sample = time_cpu_port(8, 2, 2, args.loc)  # ~10 s of host work on the GPU box
-        cpu_baseline = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": round(cms, 2)}
+        cpu_baseline = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": round(cms, 2),
+                        "relation": time_cpu_rel()}
 
     if rank == 0:
         line = {
