@@ -43,6 +43,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
     __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
+    __shared__ unsigned char s_lvl[kMaxLevels * kMaxPoints];  // level of sample slot lp (= lp / P)
     __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
     __shared__ int s_b[THREADS / (D / CH)];
     const float inv_P = 1.0f / (float)P;
@@ -59,6 +60,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
         s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
     }
+    for (int i = threadIdx.x; i < L * P; i += THREADS) s_lvl[i] = (unsigned char)(i / P);
     __syncthreads();
 
     const long long pair0 = (long long)blockIdx.x * kPairs;
@@ -95,10 +97,9 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         }
         __syncthreads();
     }
-    for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
-        const int pair = s / LP;
-        const int lp = s - pair * LP;
-        const int l = lp / P;
+    for (SampleWalk sw(threadIdx.x, kBwdThreads, LP); sw.s < nsamples; sw.next(kBwdThreads)) {
+        const int s = sw.s, pair = sw.pair, lp = sw.lp;
+        const int l = s_lvl[lp];
         float2 xy;
         float a;
         long long bq = 0;
@@ -211,10 +212,9 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
             if (slane == 0 && spair < npairs) s_stat[spair].x = dot;
         }
         __syncthreads();
-        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
-            const int pr = s / LP;
-            const int lp = s - pr * LP;
-            const int l = lp / P;
+        for (SampleWalk sw(threadIdx.x, kBwdThreads, LP); sw.s < nsamples; sw.next(kBwdThreads)) {
+            const int s = sw.s, pr = sw.pair, lp = sw.lp;
+            const int l = s_lvl[lp];
             const float4 r = s_meta[pr * stride + lp];
             const long long gs = pair0 * LP + s;
             const float glx = (float)s_W[l] * r.x, gly = (float)s_H[l] * r.y;  // d/d(loc), as the plain path returns it
@@ -234,10 +234,9 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     } else {
         float2 *gl2 = reinterpret_cast<float2 *>(io.grad_loc) + pair0 * LP;
         float *ga0 = io.grad_attn + pair0 * LP;
-        for (int s = threadIdx.x; s < nsamples; s += kBwdThreads) {
-            const int pr = s / LP;
-            const int lp = s - pr * LP;
-            const int l = lp / P;
+        for (SampleWalk sw(threadIdx.x, kBwdThreads, LP); sw.s < nsamples; sw.next(kBwdThreads)) {
+            const int s = sw.s, pr = sw.pair, lp = sw.lp;
+            const int l = s_lvl[lp];
             const float4 r = s_meta[pr * stride + lp];
             gl2[s] = make_float2((float)s_W[l] * r.x, (float)s_H[l] * r.y);
             ga0[s] = r.z;

@@ -42,6 +42,7 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
     __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
+    __shared__ unsigned char s_lvl[kMaxLevels * kMaxPoints];  // level of sample slot lp (= lp / P)
     __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
     __shared__ int s_b[THREADS / (D / CH)];
     const float inv_P = 1.0f / (float)P;
@@ -58,6 +59,7 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
         s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
     }
+    for (int i = threadIdx.x; i < L * P; i += THREADS) s_lvl[i] = (unsigned char)(i / P);
     __syncthreads();
 
     const long long pair0 = (long long)blockIdx.x * kPairs;
@@ -95,10 +97,9 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         }
         __syncthreads();
     }
-    for (int s = threadIdx.x; s < nsamples; s += kFwdThreads) {
-        const int pair = s / LP;
-        const int lp = s - pair * LP;
-        const int l = lp / P;
+    for (SampleWalk sw(threadIdx.x, kFwdThreads, LP); sw.s < nsamples; sw.next(kFwdThreads)) {
+        const int s = sw.s, pair = sw.pair, lp = sw.lp;
+        const int l = s_lvl[lp];
         float2 xy;
         float a;
         long long bq = 0;
