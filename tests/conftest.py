@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Fresh clone: build the CUDA library (nvcc, sm_100a, no GPU needed) and the C oracle once, so that no
+    test depends on another having built them.  Failures surface in the tests that need the artefacts."""
+    try:
+        from relation_detr_b200 import build
+        build.build()
+    except Exception as e:  # noqa: BLE001
+        print(f"[conftest] librdetr_ops.so not built: {e}")
+    try:
+        from oracle import c_oracle
+        c_oracle.build()
+    except Exception as e:  # noqa: BLE001
+        print(f"[conftest] librdetr_oracle.so not built: {e}")
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
 
