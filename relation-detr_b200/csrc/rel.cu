@@ -151,6 +151,29 @@ __device__ __forceinline__ void project(const float2 (*s_wt2)[kRelHeads], int n,
     }
 }
 
+// Scalar twin of project() (plain FFMA, accumulators as float): selected with -DRDETR_REL_SCALAR_FMA for
+// A/B measurements of the packed path.
+template <int R>
+__device__ __forceinline__ void project_scalar(const float2 (*s_wt2)[kRelHeads], int n, const float (&sn)[R], const float (&cs)[R],
+                                               float (&acc)[R][kRelHeads])
+{
+#pragma unroll
+    for (int q = 0; q < kRelHeads / 2; ++q) {
+        const float4 ws = *reinterpret_cast<const float4 *>(&s_wt2[n][2 * q]);      // {w_h, w_h, w_h+1, w_h+1}
+        const float4 wc = *reinterpret_cast<const float4 *>(&s_wt2[n + 1][2 * q]);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            acc[r][2 * q] = fmaf(ws.x, sn[r], acc[r][2 * q]);
+            acc[r][2 * q + 1] = fmaf(ws.z, sn[r], acc[r][2 * q + 1]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            acc[r][2 * q] = fmaf(wc.x, cs[r], acc[r][2 * q]);
+            acc[r][2 * q + 1] = fmaf(wc.z, cs[r], acc[r][2 * q + 1]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward.  CTA = 4 warps, tile = 32 tgt columns (lanes) x kFwdRowsPerCta src rows; each warp walks
 // its rows kRowsPerIter at a time.  src rows are staged once per CTA in shared memory.
@@ -222,11 +245,21 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
         const int i0 = i_cta + lrow;
         if (i0 >= N1) break;  // warp-uniform
 
+#ifdef RDETR_REL_SCALAR_FMA
+        float acc[R][kRelHeads];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int h = 0; h < kRelHeads; ++h) acc[r][h] = s_bias[h];
+#define RDETR_PROJECT project_scalar<R>
+#else
         f32x2 acc[R / 2][kRelHeads];
 #pragma unroll
         for (int p = 0; p < R / 2; ++p)
 #pragma unroll
             for (int h = 0; h < kRelHeads; ++h) acc[p][h] = pack2(s_bias[h], s_bias[h]);
+#define RDETR_PROJECT project<R>
+#endif
 
         // ---- centre features c = 0, 1 ----
 #pragma unroll 1
@@ -246,7 +279,7 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                 float sn[R], cs[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) angle_sincos<FAST>(es[r], s_d[k], s_invd[k], sn[r], cs[r]);
-                project<R>(s_wt, c * 2 * kRelK + 2 * k, sn, cs, acc);
+                RDETR_PROJECT(s_wt, c * 2 * kRelK + 2 * k, sn, cs, acc);
             }
         }
         // ---- size features c = 2, 3 ----
@@ -273,7 +306,7 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                             sn[r] = fmaf(sA, cBk, -(cA * sBk));  // sin(A - B)
                             cs[r] = fmaf(cA, cBk, sA * sBk);     // cos(A - B)
                         }
-                        project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+                        RDETR_PROJECT(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
                     }
                 }
             } else {
@@ -286,7 +319,7 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                     float sn[R], cs[R];
 #pragma unroll
                     for (int r = 0; r < R; ++r) angle_sincos<false>(es[r], s_d[k], s_invd[k], sn[r], cs[r]);
-                    project<R>(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
+                    RDETR_PROJECT(s_wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
                 }
             }
         }
@@ -300,9 +333,13 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
             uint32_t words[kRelHeads];
 #pragma unroll
             for (int h = 0; h < kRelHeads; ++h) {
+#ifdef RDETR_REL_SCALAR_FMA
+                const float a = acc[r][h];
+#else
                 float lo, hi;
                 unpack2(acc[r >> 1][h], lo, hi);
                 const float a = (r & 1) ? hi : lo;
+#endif
                 const bool pos = jok && a > 0.f;
                 words[h] = __ballot_sync(0xffffffffu, pos);
                 if (jok) out[(((size_t)b * kRelHeads + h) * N1 + i) * N2 + j] = blocked ? -INFINITY : (pos ? a : 0.f);
