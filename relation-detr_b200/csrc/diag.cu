@@ -36,7 +36,7 @@ diag_gather_rows_kernel(const uint4 *__restrict__ table, uint32_t row_mask, int 
 }
 
 __global__ void __launch_bounds__(256)
-diag_red_rows_kernel(float *__restrict__ table, uint32_t nrows, int iters)
+diag_red_rows_kernel(float *__restrict__ table, uint32_t row_mask, int iters)
 {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t group = tid >> 3, lane = tid & 7;
@@ -44,8 +44,8 @@ diag_red_rows_kernel(float *__restrict__ table, uint32_t nrows, int iters)
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            seed = hash32(seed + u);
-            red_add_f32x4(table + (size_t)(seed % nrows) * 32 + lane * 4, 1.f, 1.f, 1.f, 1.f);
+            seed = seed * 1664525u + 1013904223u;
+            red_add_f32x4(table + (size_t)((seed >> 9) & row_mask) * 32 + lane * 4, 1.f, 1.f, 1.f, 1.f);
         }
     }
 }
@@ -79,7 +79,9 @@ extern "C" int rdetr_diag_red_rows(void *table, long long nrows, int iters, long
     const DeviceGuard guard(table);
     if (guard.status()) return guard.status();
     const int blocks = 148 * 16, threads = 256;
-    diag_red_rows_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float *>(table), (uint32_t)nrows, iters);
+    uint32_t pow2 = 1;
+    while ((long long)pow2 * 2 <= nrows) pow2 *= 2;
+    diag_red_rows_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<float *>(table), pow2 - 1, iters);
     if (rows_out) *rows_out = (long long)blocks * threads / 8 * iters * 8;
     return check_cuda(cudaGetLastError(), "diag_red_rows_kernel launch");
 }
