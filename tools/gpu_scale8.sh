@@ -8,6 +8,6 @@ import json
 d=json.loads(open("gpurun_out/bench_n$N.json").read().strip().splitlines()[-1])
 print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "cpu", d["cpu_baseline"])
 PY
-for prec in "" "--bf16"; do
+for prec in "" "--bf16" "--backbone" "--backbone --bf16"; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29562 tools/train_proxy.py $prec 2>gpurun_out/tp_err_$N.log | grep '^{' | tee -a gpurun_out/train_proxy_n$N.jsonl | cut -c100-400
 done

@@ -3,7 +3,7 @@
 N=$(nvidia-smi -L | wc -l)
 mkdir -p gpurun_out
 : > gpurun_out/train_proxy.jsonl
-for prec in "" "--tf32" "--bf16" "--graph" "--graph --bf16"; do
+for prec in "" "--bf16" "--graph --bf16" "--backbone" "--backbone --bf16"; do
   timeout 200 python tools/train_proxy.py $prec 2>/dev/null | grep '^{' >> gpurun_out/train_proxy.jsonl
   for n in 2 4 8; do
     if [ $n -le $N ]; then

@@ -43,14 +43,43 @@ class EncoderLayer(nn.Module):
         return self.norm2(x + self.linear2(torch.relu(self.linear1(x))))
 
 
-class TransformerProxy(nn.Module):
-    def __init__(self, levels=4):
+class BackboneNeck(nn.Module):
+    """What feeds the transformer in configs[3]: torchvision ResNet-50 (random init, frozen BN, stem + layer1
+    frozen as upstream does) -> C3..C5 -> 1x1 conv + GroupNorm to 256 channels, plus a stride-2 3x3 conv level
+    (call pattern of models/necks/channel_mapper.py).  Library code (cuDNN), not part of the hot path."""
+
+    def __init__(self, d=256):
         super().__init__()
+        import torchvision
+        from torchvision.ops.misc import FrozenBatchNorm2d
+
+        r = torchvision.models.resnet50(weights=None, norm_layer=FrozenBatchNorm2d)
+        self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool, r.layer1)
+        for p in self.stem.parameters():
+            p.requires_grad_(False)
+        self.layer2, self.layer3, self.layer4 = r.layer2, r.layer3, r.layer4
+        self.lateral = nn.ModuleList([nn.Sequential(nn.Conv2d(c, d, 1), nn.GroupNorm(32, d)) for c in (512, 1024, 2048)])
+        self.extra = nn.Sequential(nn.Conv2d(2048, d, 3, stride=2, padding=1), nn.GroupNorm(32, d))
+
+    def forward(self, images):
+        with torch.no_grad():
+            x = self.stem(images)
+        c3 = self.layer2(x)
+        c4 = self.layer3(c3)
+        c5 = self.layer4(c4)
+        feats = [lat(c) for lat, c in zip(self.lateral, (c3, c4, c5))] + [self.extra(c5)]
+        return torch.cat([f.flatten(2).transpose(1, 2) for f in feats], 1)  # [B, S, 256]
+
+
+class TransformerProxy(nn.Module):
+    def __init__(self, levels=4, backbone=False):
+        super().__init__()
+        self.backbone = BackboneNeck() if backbone else None
         self.encoder = nn.ModuleList([EncoderLayer(levels=levels) for _ in range(6)])
         self.decoder = dh.RelationDecoder("ours", levels=levels)  # shared by the main and the hybrid pass, as upstream
 
     def forward(self, feats, pos, ref2d, ss, lsi, main, hybrid):
-        x = feats
+        x = self.backbone(feats) if self.backbone is not None else feats  # feats = images when the backbone is on
         for layer in self.encoder:
             x = layer(x, pos, ref2d, ss, lsi, None)
         c1, b1 = self.decoder(main["query"], main["reference_points"], x, ss, lsi, main["valid_ratios"], main["attn_mask"])
@@ -66,6 +95,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--bf16", action="store_true")
     ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--backbone", action="store_true", help="prepend ResNet-50 + channel mapper on 800x1344 images")
     ap.add_argument("--graph", action="store_true", help="capture the whole step (fwd+bwd+clip+AdamW) in one CUDA graph")
     args = ap.parse_args()
     rank, local_rank, world = rdist.env_rank_world()
@@ -75,15 +105,16 @@ def main():
         rdist.init_process_group("nccl")
     torch.backends.cuda.matmul.allow_tf32 = args.tf32
     torch.manual_seed(0)
-    model = TransformerProxy().to(dev)
+    model = TransformerProxy(backbone=args.backbone).to(dev)
     nparams = sum(p.numel() for p in model.parameters())
     ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=False) if world > 1 else model
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, capturable=args.graph)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4, capturable=args.graph)
     levels = workloads.LEVELS_800_1333
     ss, lsi = workloads.shape_tensors(levels, dev)
     S = int(ss.prod(1).sum())
     g = torch.Generator(device=dev).manual_seed(100 + rank)  # each rank owns its own images
-    feats = torch.randn((args.batch, S, 256), device=dev, generator=g)
+    feats = (torch.randn((args.batch, 3, 800, 1344), device=dev, generator=g) if args.backbone
+             else torch.randn((args.batch, S, 256), device=dev, generator=g))
     pos = torch.randn((args.batch, S, 256), device=dev, generator=g)
     ref2d = workloads.full_reference_points(levels, dev)[None, :, None, :].expand(args.batch, -1, 4, -1).contiguous()
     main_in = dh.make_inputs(args.batch, 900, 200, levels, seed=rank, device=dev)
@@ -94,7 +125,7 @@ def main():
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
             loss = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
         opt.step()
         return loss
 
@@ -114,7 +145,7 @@ def main():
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
                 static_loss = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)
             static_loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
             opt.step()
 
         def step():  # noqa: F811
@@ -134,7 +165,8 @@ def main():
     rdist.barrier()
     ms = rdist.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     if rank == 0:
-        print(json.dumps({"workload": "train_proxy: 6-layer deformable encoder + relation decoder (main + hybrid), fwd+bwd+AdamW, DDP/NCCL",
+        print(json.dumps({"workload": ("train_proxy: " + ("ResNet-50 + channel mapper (800x1344 images) + " if args.backbone else "")
+                                       + "6-layer deformable encoder + relation decoder (main + hybrid), fwd+bwd+AdamW, DDP/NCCL"),
                           "n_gpus": world, "batch_per_gpu": args.batch, "precision": "bf16 autocast" if args.bf16 else ("tf32 matmul" if args.tf32 else "fp32"),
                           "cuda_graph": bool(args.graph), "params_M": round(nparams / 1e6, 2), "ms_per_step": round(ms, 3),
                           "imgs_per_s": round(world * args.batch / ms * 1e3, 2), "loss": float(loss.detach())}))
