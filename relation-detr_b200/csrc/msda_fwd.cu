@@ -71,7 +71,8 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     float2 *s_stat = reinterpret_cast<float2 *>(s_wgt + kPairs * stride);  // FusedIO: per-pair (max, sum) of the softmax
     if constexpr (IO::kFused) {
         // softmax statistics of every pair: its kLanes lanes (the same lanes that gather for it in phase 2)
-        // split the L*P logits and combine with xor-shuffles -- no shared-memory staging, one barrier
+        // split the L*P logits (streamed once, kept in the sample's shared-memory slot for the main loop) and
+        // combine max / sum with xor-shuffles; one barrier
         const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
         const auto *zrow = io.logits + (pair0 + (spair < npairs ? spair : 0)) * LP;
         float4 *zslot = s_wgt + (spair < npairs ? spair : 0) * stride;  // .x of every slot keeps the logit for the main loop
