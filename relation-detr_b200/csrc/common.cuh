@@ -269,6 +269,75 @@ __device__ __forceinline__ float2 fused_location(const float *rp, int ref_dim, f
     return make_float2(fmaf((offx * invP) * rp[2], 0.5f, rp[0]), fmaf((offy * invP) * rp[3], 0.5f, rp[1]));
 }
 
+// ---- pieces of phase 1 shared by the forward and the backward kernel ------------------------------
+
+// FusedIO only.  Softmax statistics (max, sum of exp) of every pair of the CTA: the pair's kLanes lanes split
+// its L*P logits -- streamed once and parked in `.x` of the sample's shared-memory slot for the main loop --
+// and combine with xor-shuffles.  Also records b*Nq+q and b per pair so that the 64-bit divisions happen once
+// per pair, not once per sample.  Every thread of the CTA must call it; ends with a barrier.
+template <int kLanes, typename IO>
+__device__ __forceinline__ void fused_softmax_stats(const IO &io, long long pair0, int npairs, int LP, int M, int Nq,
+                                                    float4 *slots, int stride, float2 *s_stat, long long *s_bq, int *s_b)
+{
+    const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
+    const bool live = spair < npairs;
+    const auto *zrow = io.logits + (pair0 + (live ? spair : 0)) * LP;
+    float4 *zslot = slots + (live ? spair : 0) * stride;
+    float mx = -INFINITY;
+    if (live)
+        for (int lp = slane; lp < LP; lp += kLanes) {
+            const float z = ld_stream_scalar(zrow + lp);
+            zslot[lp].x = z;
+            mx = fmaxf(mx, z);
+        }
+#pragma unroll
+    for (int off = kLanes / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    if (live)
+        for (int lp = slane; lp < LP; lp += kLanes) sum += __expf(zslot[lp].x - mx);
+#pragma unroll
+    for (int off = kLanes / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (slane == 0 && live) {
+        s_stat[spair] = make_float2(mx, sum);
+        const long long bq = (pair0 + spair) / M;
+        s_bq[spair] = bq;
+        s_b[spair] = (int)(bq / Nq);
+    }
+    __syncthreads();
+}
+
+// Attention weight and bilinear tap of sample (pair, lp) of the CTA, from either source of inputs.
+//   PlainIO: streamed from sampling_locations / attention_weights.
+//   FusedIO: softmax from the parked logit and the pair's statistics, location from reference point + offset,
+//            corners on padded pixels invalidated (value.masked_fill of the reference, ms_deform_attn.py:318-319).
+template <typename IO>
+__device__ __forceinline__ Tap sample_tap(const IO &io, long long pair0, int s, int pair, int lp, int l, int LP, int L, int S,
+                                          float logit_x, const float2 *s_stat, const long long *s_bq, const int *s_b,
+                                          const int *s_H, const int *s_W, const int *s_start, const float *s_invW,
+                                          const float *s_invH, float inv_P, float &a)
+{
+    float2 xy;
+    if constexpr (IO::kFused) {
+        const float2 st = s_stat[pair];
+        a = __expf(logit_x - st.x) / st.y;  // exp(z - max) / sum with the MUFU exponential (2 ulp)
+        const float2 off = ld_stream_pair(io.offsets + 2 * (pair0 * LP + s));
+        xy = fused_location(io.ref + (s_bq[pair] * L + l) * io.ref_dim, io.ref_dim, off.x, off.y, s_invW[l], s_invH[l], inv_P);
+    } else {
+        xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
+        a = ld_stream_f1(io.attn + pair0 * LP + s);
+    }
+    Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+    if constexpr (IO::kFused) {
+        if (io.mask != nullptr) {
+            const uint8_t *mrow = io.mask + (long long)s_b[pair] * S;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;
+        }
+    }
+    return t;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace rdetr

@@ -70,59 +70,12 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     // ---- phase 1 -----------------------------------------------------------------------------------
     float2 *s_stat = reinterpret_cast<float2 *>(s_meta + kPairs * stride);  // FusedIO: per-pair softmax statistics
-    if constexpr (IO::kFused) {
-        // softmax statistics per pair: kLanes lanes split the L*P logits, xor-shuffle reduction (see msda_fwd.cu)
-        const int spair = threadIdx.x / kLanes, slane = threadIdx.x - spair * kLanes;
-        const auto *zrow = io.logits + (pair0 + (spair < npairs ? spair : 0)) * LP;
-        float4 *zslot = s_meta + (spair < npairs ? spair : 0) * stride;  // .x of every slot keeps the logit for the main loop
-        float mx = -INFINITY;
-        if (spair < npairs)
-            for (int lp = slane; lp < LP; lp += kLanes) {
-                const float z = ld_stream_scalar(zrow + lp);
-                zslot[lp].x = z;
-                mx = fmaxf(mx, z);
-            }
-#pragma unroll
-        for (int off = kLanes / 2; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        float sum = 0.f;
-        if (spair < npairs)
-            for (int lp = slane; lp < LP; lp += kLanes) sum += __expf(zslot[lp].x - mx);
-#pragma unroll
-        for (int off = kLanes / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (slane == 0 && spair < npairs) {
-            s_stat[spair] = make_float2(mx, sum);
-            const long long bq_ = (pair0 + spair) / M;
-            s_bq[spair] = bq_;
-            s_b[spair] = (int)(bq_ / Nq);
-        }
-        __syncthreads();
-    }
+    if constexpr (IO::kFused) fused_softmax_stats<kLanes>(io, pair0, npairs, LP, M, Nq, s_meta, stride, s_stat, s_bq, s_b);
     for (SampleWalk sw(threadIdx.x, kBwdThreads, LP); sw.s < nsamples; sw.next(kBwdThreads)) {
-        const int s = sw.s, pair = sw.pair, lp = sw.lp;
-        const int l = s_lvl[lp];
-        float2 xy;
+        const int pair = sw.pair, lp = sw.lp, l = s_lvl[lp];
         float a;
-        long long bq = 0;
-        if constexpr (IO::kFused) {
-            const float2 st = s_stat[pair];
-            a = __expf(s_meta[pair * stride + lp].x - st.x) / st.y;
-            bq = s_bq[pair];
-            const long long gs = pair0 * LP + s;
-            const float2 off = ld_stream_pair(io.offsets + 2 * gs);
-            xy = fused_location(io.ref + (bq * L + l) * io.ref_dim, io.ref_dim, off.x, off.y, s_invW[l], s_invH[l], inv_P);
-        } else {
-            xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
-            a = ld_stream_f1(io.attn + pair0 * LP + s);
-        }
-        Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
-        if constexpr (IO::kFused) {
-            if (io.mask != nullptr) {
-                const uint8_t *mrow = io.mask + (long long)s_b[pair] * S;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (t.pix[i] >= 0 && mrow[t.pix[i]]) t.pix[i] = -1;
-            }
-        }
+        const Tap t = sample_tap(io, pair0, sw.s, pair, lp, l, LP, L, S, s_meta[pair * stride + lp].x, s_stat, s_bq, s_b, s_H, s_W,
+                                 s_start, s_invW, s_invH, inv_P, a);
         s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
         s_meta[pair * stride + lp] = make_float4(t.lw, t.lh, a, 0.f);
     }
