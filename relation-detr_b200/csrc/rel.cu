@@ -180,7 +180,8 @@ __device__ __forceinline__ void project_scalar(const float2 (*s_wt2)[kRelHeads],
 // relu_bits layout: [B][N1][ceil(N2/32)][H] words (the 8 heads of one (row, column word) contiguous).
 // ------------------------------------------------------------------------------------------------
 constexpr int kRelFwdWarps = 4;
-constexpr int kRowsPerIter = 4;
+constexpr int kRowsPerIter = 4;       // FAST: rows per thread and iteration (2: 0.326 ms, 4: 0.300, 8: 0.303 at N=900)
+constexpr int kRowsPerIterExact = 2;  // EXACT: the sincosf-heavy body prefers fewer registers (2: 0.58 ms, 4: 0.62, 8: 0.83)
 constexpr int kFwdRowsPerWarp = 16;
 constexpr int kFwdRowsPerCta = kRelFwdWarps * kFwdRowsPerWarp;
 
@@ -191,7 +192,7 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                const float *__restrict__ dim_t, float scale, float eps, const uint8_t *__restrict__ mask,
                float *__restrict__ out, uint32_t *__restrict__ relu_bits, int N1, int N2)
 {
-    constexpr int R = kRowsPerIter;
+    constexpr int R = FAST ? kRowsPerIter : kRowsPerIterExact;
     constexpr int kRowF = FAST ? kTab : 4;  // floats staged per src row
     __shared__ __align__(16) float2 s_wt[kRelFeat][kRelHeads];  // transposed and duplicated: [n][h] = {w, w}
     __shared__ __align__(16) float s_row[kFwdRowsPerCta][kRowF];
