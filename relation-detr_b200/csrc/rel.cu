@@ -476,12 +476,14 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
         }
         __syncthreads();
 
-        // two rows per iteration: two independent feature chains in flight per lane (the kernel is
-        // latency bound at 2 CTAs/SM otherwise); rows past `trows` read zeroed s_g / padded s_row
-        for (int r = 0; r < trows; r += 2) {
-            float f[2][8];
+        // FAST: two rows per iteration (two independent feature chains in flight per lane; the kernel is latency
+        // bound at 2 CTAs/SM otherwise).  EXACT: one row -- two inlined sincosf bodies per iteration are ~120 KB of
+        // SASS and stall on instruction fetch.  Rows past `trows` read zeroed s_g / padded s_row.
+        constexpr int U = FAST ? 2 : 1;
+        for (int r = 0; r < trows; r += U) {
+            float f[U][8];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const float *row = s_row[t0 + r + u];
                 if constexpr (FAST) {
                     if (c < 2) {
@@ -507,10 +509,17 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
             }
 #pragma unroll
             for (int h = 0; h < kRelHeads; ++h) {
-                const float g0 = s_g[buf][r][h][lane], g1 = s_g[buf][r + 1][h][lane];
+                if constexpr (U == 2) {
+                    const float g0 = s_g[buf][r][h][lane], g1 = s_g[buf][r + 1][h][lane];
 #pragma unroll
-                for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g1, f[1][n], fmaf(g0, f[0][n], acc[h][n]));
-                if (w == 0) accb[h] += g0 + g1;  // grad_bias is accumulated by one warp only (warp-uniform branch)
+                    for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g1, f[1][n], fmaf(g0, f[0][n], acc[h][n]));
+                    if (w == 0) accb[h] += g0 + g1;  // grad_bias is accumulated by one warp only (warp-uniform branch)
+                } else {
+                    const float g0 = s_g[buf][r][h][lane];
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) acc[h][n] = fmaf(g0, f[0][n], acc[h][n]);
+                    if (w == 0) accb[h] += g0;
+                }
             }
         }
         __syncthreads();  // every warp is done with tile `buf` before the copy after next overwrites it
