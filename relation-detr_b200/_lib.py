@@ -12,6 +12,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDETR_OPS_LIB", os.path.join(PKG_DIR, "librdetr_ops.so"))
 
+ABI_VERSION = 1  # RDETR_ABI_VERSION in include/rdetr_ops.h
 DTYPE_F32, DTYPE_BF16 = 0, 1
 REL_EXACT, REL_FAST = 0, 1
 
@@ -55,6 +56,9 @@ def lib() -> ctypes.CDLL:
                     fn = getattr(handle, name)  # AttributeError if the .so does not export it
                     fn.restype = res
                     fn.argtypes = args
+                if handle.rdetr_abi_version() != ABI_VERSION:
+                    raise RuntimeError(f"{LIB_PATH} reports ABI version {handle.rdetr_abi_version()}, this package binds "
+                                       f"version {ABI_VERSION}: rebuild with `python -m relation_detr_b200.build --force`")
                 _lib = handle
     return _lib
 
