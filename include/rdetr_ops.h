@@ -164,6 +164,31 @@ int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, cons
                             size_t workspace_bytes, rdetr_stream_t stream);
 
 /*
+ * Batched rectangular linear-sum-assignment.
+ * Replaces scipy.optimize.linear_sum_assignment(c.cpu()) at models/matcher/hungarian_matcher.py:80 and :87
+ * (one device->host copy + host solve per image and per decoder layer).  All problems of one call are
+ * solved by one launch (one CTA per problem; 64 problems per launch) on `stream`; nothing synchronises.
+ *
+ *   cost[p]     device, float32 [n_rows[p], n_cols[p]] row-major (the matcher's cost matrix, queries x boxes)
+ *   row_ind[p]  device, int64 [min(n_rows[p], n_cols[p])]: input rows of the pairs, ascending
+ *   col_ind[p]  device, int64, same length: the column matched to each of those rows
+ *   status      device, int32 [n_problems]: 0 ok, 1 infeasible, 2 NaN / -inf entry (SciPy raises ValueError
+ *               for both); on 1 and 2 the index buffers are filled with -1
+ *   cost, n_rows, n_cols, row_ind, col_ind are HOST arrays of n_problems entries (pointers / extents).
+ *
+ * The optimum returned is the one SciPy returns, ties included: the kernel restates SciPy's shortest-
+ * augmenting-path solver (Crouse 2016) with its scan order, in double precision on the float32 costs.
+ * Limits: rows*cols < 2^31 and 29*max(rows,cols) + 13*min(rows,cols) + 16 <= 204800 bytes per problem
+ * (state in shared memory; 1500 x 600 needs 51 KB) -> RDETR_ERR_UNSUPPORTED.
+ * Workspace: rdetr_lsap_workspace_bytes() bytes of device memory (a transposed float32 copy of every
+ * problem with more rows than columns), 256-byte aligned.
+ */
+size_t rdetr_lsap_workspace_bytes(const int64_t *n_rows, const int64_t *n_cols, int n_problems);
+int rdetr_lsap_solve(const float *const *cost, const int64_t *n_rows, const int64_t *n_cols,
+                     int64_t *const *row_ind, int64_t *const *col_ind, int32_t *status, int n_problems,
+                     void *workspace, size_t workspace_bytes, rdetr_stream_t stream);
+
+/*
  * Diagnostics (not on the product path): measure on the current device the two hardware rates that
  * bound the MSDA kernels -- random 128-byte row gathers (8 lanes x 16-byte read-only loads per row) and
  * 128-byte vector reductions (red.global.add.v4.f32) -- over a caller-provided table of nrows rows.

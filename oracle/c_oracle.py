@@ -18,7 +18,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compile the C oracle with the committed Makefile (gcc, seconds)."""
-    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("rdetr_oracle.c", "rdetr_oracle_impl.inc"))
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("rdetr_oracle.c", "rdetr_oracle_impl.inc", "lsap_oracle.c"))
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < src_m:
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _SO
@@ -27,8 +27,7 @@ def build(force: bool = False) -> str:
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()
         _lib = ctypes.CDLL(_SO)
         _lib.rdetr_oracle_set_threads.restype = ctypes.c_int
         _lib.rdetr_oracle_set_threads.argtypes = [ctypes.c_int]
@@ -122,3 +121,21 @@ def rel_backward(src_boxes, tgt_boxes, weight, bias, dim_t, grad_out, scale=100.
     fn(_p(src), _p(tgt), _p(w), _p(b_), _p(d), creal(scale), creal(eps), _p(go), _p(gw), _p(gb),
        *(ctypes.c_int(int(x)) for x in (B, N1, N2, H, K)))
     return gw, gb
+
+
+def lsap(cost):
+    """cost [n_rows, n_cols] -> (row_ind, col_ind) int64, the pairs scipy.optimize.linear_sum_assignment
+    returns for the same matrix (hungarian_matcher.py:80).  Raises ValueError like SciPy on an infeasible
+    matrix or a NaN / -inf entry.  See lsap_oracle.c for what is restated and how it is pinned."""
+    c = np.ascontiguousarray(np.asarray(cost), dtype=np.float64)
+    assert c.ndim == 2
+    n = min(c.shape)
+    rows, cols = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    fn = lib().rdetr_oracle_lsap
+    fn.restype = ctypes.c_int
+    rc = fn(_p(c), ctypes.c_int64(c.shape[0]), ctypes.c_int64(c.shape[1]), _p(rows), _p(cols))
+    if rc == -1:
+        raise ValueError("cost matrix is infeasible")
+    if rc == -2:
+        raise ValueError("matrix contains invalid numeric entries")
+    return rows, cols

@@ -12,6 +12,7 @@ library, or with non-CUDA tensors, raises.
 __version__ = "0.1.0"
 
 from . import ops, workloads  # noqa: E402,F401
+from .matcher import HungarianMatcher  # noqa: E402,F401
 from .modules import MultiScaleDeformableAttention, PositionRelationEmbedding  # noqa: E402,F401
 from .ops import (MultiScaleDeformableAttnFunction, ms_deform_attn, position_relation_bias,  # noqa: E402,F401
                   relation_dim_t)

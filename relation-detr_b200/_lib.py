@@ -28,6 +28,8 @@ _SIGNATURES = {
     "rdetr_relation_workspace_bytes": (c_size_t, [c_int] * 4),
     "rdetr_relation_forward": (c_int, [c_void_p] * 5 + [c_float, c_float] + [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_relation_backward": (c_int, [c_void_p] * 3 + [c_float, c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
+    "rdetr_lsap_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_int]),
+    "rdetr_lsap_solve": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_size_t, c_void_p]),
     "rdetr_diag_gather_rows": (c_int, [c_void_p, c_longlong, c_int, c_void_p, ctypes.POINTER(c_longlong), c_void_p]),
     "rdetr_diag_red_rows": (c_int, [c_void_p, c_longlong, c_int, ctypes.POINTER(c_longlong), c_void_p]),
 }

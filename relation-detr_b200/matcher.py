@@ -1,0 +1,129 @@
+"""Device-resident ``HungarianMatcher`` -- the reference's matcher without its host round trip.
+
+Mirrors ``models/matcher/hungarian_matcher.py`` of the reference (same constructor arguments, same
+``calculate_*`` methods, same ``forward`` signature and result order).  The cost matrix is computed by the
+same torch operations on the device, as upstream does; what changes is line 80 / 87: instead of
+``linear_sum_assignment(c.cpu())`` -- a device->host copy that stalls the stream once per image and per
+decoder layer -- the matrix is handed to ``rdetr_lsap_solve`` and the index tensors stay on the device.
+Results are the pairs SciPy returns for the same matrix, ties included (tests/test_lsap_gpu.py).
+
+Differences, deliberate:
+* the two index tensors are CUDA int64 tensors (upstream: CPU tensors); every use in
+  ``models/bricks/set_criterion.py`` (:53-54, :90-92, :110-117) indexes device tensors with them, which
+  now needs no implicit host->device copy either;
+* SciPy's ``ValueError`` for an infeasible matrix / a NaN entry cannot be raised without synchronising.
+  ``check_status=True`` restores it (one sync per call); by default the solver's status word stays on the
+  device in ``last_status`` and failed problems return ``-1`` indices;
+* ``match_batch`` solves all images of one prediction set in a single launch (upstream: ``map`` over images).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+
+
+def _cxcywh_to_xyxy(b: Tensor) -> Tensor:
+    # torchvision.ops.boxes._box_cxcywh_to_xyxy, operation for operation (same rounding)
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), dim=-1)
+
+
+def _generalized_box_iou(b1: Tensor, b2: Tensor) -> Tensor:
+    # torchvision.ops.generalized_box_iou for floating-point boxes, operation for operation
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = torch.max(b1[:, None, :2], b2[:, :2])
+    rb = torch.min(b1[:, None, 2:], b2[:, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[:, :, 0] * wh[:, :, 1]
+    union = area1[:, None] + area2 - inter
+    iou = inter / union
+    lti = torch.min(b1[:, None, :2], b2[:, :2])
+    rbi = torch.max(b1[:, None, 2:], b2[:, 2:])
+    whi = (rbi - lti).clamp(min=0)
+    areai = whi[:, :, 0] * whi[:, :, 1]
+    return iou - (areai - union) / areai
+
+
+class HungarianMatcher(nn.Module):
+    """Drop-in for ``models.matcher.hungarian_matcher.HungarianMatcher`` (hungarian_matcher.py:8-91)."""
+
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha: float = 0.25,
+                 focal_gamma: float = 2.0, mixed_match: bool = False, check_status: bool = False):
+        super().__init__()
+        self.cost_class = cost_class
+        self.cost_bbox = cost_bbox
+        self.cost_giou = cost_giou
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
+        self.focal_alpha = focal_alpha
+        self.focal_gamma = focal_gamma
+        self.mixed_match = mixed_match
+        self.check_status = check_status
+        self.last_status = None
+
+    # -- cost terms: hungarian_matcher.py:40-72, same operations in the same order -----------------------
+    def calculate_class_cost(self, pred_logits, gt_labels, **kwargs):
+        out_prob = pred_logits.sigmoid()
+        neg_cost_class = -(1 - self.focal_alpha) * out_prob**self.focal_gamma * (1 - out_prob + 1e-6).log()
+        pos_cost_class = -self.focal_alpha * (1 - out_prob)**self.focal_gamma * (out_prob + 1e-6).log()
+        return pos_cost_class[:, gt_labels] - neg_cost_class[:, gt_labels]
+
+    def calculate_bbox_cost(self, pred_boxes, gt_boxes, **kwargs):
+        return torch.cdist(pred_boxes, gt_boxes, p=1)
+
+    def calculate_giou_cost(self, pred_boxes, gt_boxes, **kwargs):
+        return -_generalized_box_iou(_cxcywh_to_xyxy(pred_boxes), _cxcywh_to_xyxy(gt_boxes))
+
+    @torch.no_grad()
+    def calculate_cost(self, pred_boxes: Tensor, pred_logits: Tensor, gt_boxes: Tensor, gt_labels: Tensor):
+        cost_class = self.calculate_class_cost(pred_logits, gt_labels)
+        cost_bbox = self.calculate_bbox_cost(pred_boxes, gt_boxes)
+        cost_giou = self.calculate_giou_cost(pred_boxes, gt_boxes)
+        return self.cost_bbox * cost_bbox + self.cost_class * cost_class + self.cost_giou * cost_giou
+
+    # -- assignment ----------------------------------------------------------------------------------------
+    def _prepare(self, c: Tensor, gt_copy: int) -> Tuple[Tensor, int]:
+        if not self.mixed_match:
+            return c.float(), 0
+        gt_size = c.size(-1)
+        num_queries = len(c)
+        gt_copy = min(int(num_queries * 0.5 / gt_size), gt_copy) if gt_size > 0 else gt_copy
+        return c.float().repeat(1, gt_copy), gt_size
+
+    def _finish(self, src_ind: Tensor, tgt_ind: Tensor, gt_size: int) -> Tuple[Tensor, Tensor]:
+        if not self.mixed_match:
+            return src_ind, tgt_ind
+        # hungarian_matcher.py:88-91 (the sort is made stable so that the device result is defined)
+        tgt_ind = tgt_ind % gt_size if gt_size > 0 else tgt_ind
+        tgt_ind, ind = tgt_ind.sort(stable=True)
+        return src_ind[ind].view(-1), tgt_ind
+
+    def _solve(self, mats: Sequence[Tensor]):
+        pairs, status = ops.lsap_solve(mats)
+        self.last_status = status
+        if self.check_status:
+            bad = status.nonzero().flatten().tolist()   # synchronises: opt-in
+            if bad:
+                code = int(status[bad[0]])
+                raise ValueError("cost matrix is infeasible" if code == 1 else "matrix contains invalid numeric entries")
+        return pairs
+
+    @torch.no_grad()
+    def forward(self, pred_boxes: Tensor, pred_logits: Tensor, gt_boxes: Tensor, gt_labels: Tensor, gt_copy: int = 1):
+        c, gt_size = self._prepare(self.calculate_cost(pred_boxes, pred_logits, gt_boxes, gt_labels), gt_copy)
+        (src_ind, tgt_ind), = self._solve([c])
+        return self._finish(src_ind, tgt_ind, gt_size)
+
+    @torch.no_grad()
+    def match_batch(self, pred_boxes: Sequence[Tensor], pred_logits: Sequence[Tensor], gt_boxes: Sequence[Tensor],
+                    gt_labels: Sequence[Tensor], gt_copy: int = 1) -> List[Tuple[Tensor, Tensor]]:
+        """All images of one prediction set in one solver launch; same result as
+        ``list(map(self, pred_boxes, pred_logits, gt_boxes, gt_labels))`` (set_criterion.py:126)."""
+        prepared = [self._prepare(self.calculate_cost(pb, pl, gb, gl), gt_copy)
+                    for pb, pl, gb, gl in zip(pred_boxes, pred_logits, gt_boxes, gt_labels)]
+        pairs = self._solve([c for c, _ in prepared])
+        return [self._finish(s, t, g) for (s, t), (_, g) in zip(pairs, prepared)]

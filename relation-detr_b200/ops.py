@@ -14,7 +14,7 @@ PyTorch is plumbing here (device memory, streams, autograd registration); the ar
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -25,6 +25,7 @@ __all__ = [
     "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
     "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
+    "lsap_solve",
 ]
 
 
@@ -359,3 +360,43 @@ def position_relation_bias(src_boxes: Tensor, tgt_boxes: Optional[Tensor], weigh
     out, _ = relation_forward(src_boxes.detach().float().contiguous(), tgt_boxes.detach().float().contiguous(),
                               weight.float().contiguous(), bias.float().contiguous(), dim_t, scale, eps, attn_mask, fast)
     return out
+
+
+# ---- batched linear-sum-assignment -------------------------------------
+
+def lsap_solve(costs: Sequence[Tensor]) -> Tuple[List[Tuple[Tensor, Tensor]], Tensor]:
+    """Solve every cost matrix of ``costs`` (float32 CUDA tensors ``[n_rows, n_cols]``, same device) with one
+    launch of the device solver.  -> (``[(row_ind, col_ind), ...]`` int64 device tensors with the pairs
+    ``scipy.optimize.linear_sum_assignment`` returns for the same matrix, ``status`` int32 ``[len(costs)]``
+    on the device: 0 ok, 1 infeasible, 2 NaN/-inf entry).  Replaces ``linear_sum_assignment(c.cpu())``
+    (reference models/matcher/hungarian_matcher.py:80,87) without a host synchronisation: the status is
+    left on the device for the caller to inspect when it chooses to."""
+    import ctypes
+
+    costs = list(costs)
+    _require(len(costs) > 0, "rdetr::lsap: no cost matrix")
+    dev = costs[0].device
+    mats = []
+    for c in costs:
+        _require(c.is_cuda and c.device == dev, "rdetr::lsap: cost matrices must be CUDA tensors on one device (no CPU path)")
+        _require(c.dim() == 2 and c.dtype == torch.float32, f"rdetr::lsap: expected float32 [rows, cols], got {c.dtype} {tuple(c.shape)}")
+        mats.append(c.detach().contiguous())
+    P = len(mats)
+    lens = [min(c.shape) for c in mats]
+    flat = torch.empty(2 * sum(lens), dtype=torch.int64, device=dev)
+    status = torch.empty(P, dtype=torch.int32, device=dev)
+    out, cursor = [], 0
+    for n in lens:
+        out.append((flat[cursor:cursor + n], flat[cursor + n:cursor + 2 * n]))
+        cursor += 2 * n
+    n_rows = (ctypes.c_int64 * P)(*[c.shape[0] for c in mats])
+    n_cols = (ctypes.c_int64 * P)(*[c.shape[1] for c in mats])
+    cost_p = (ctypes.c_void_p * P)(*[c.data_ptr() for c in mats])
+    row_p = (ctypes.c_void_p * P)(*[r.data_ptr() for r, _ in out])
+    col_p = (ctypes.c_void_p * P)(*[c.data_ptr() for _, c in out])
+    lib = _lib.lib()
+    ws_bytes = lib.rdetr_lsap_workspace_bytes(n_rows, n_cols, P)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    _lib.check(lib.rdetr_lsap_solve(cost_p, n_rows, n_cols, row_p, col_p, _ptr(status), P, _ptr(ws), ws_bytes, _stream(status)),
+               "rdetr_lsap_solve")
+    return out, status

@@ -1,0 +1,137 @@
+"""GPU: rdetr_lsap_solve / HungarianMatcher against SciPy (the solver the reference calls,
+hungarian_matcher.py:80,87), the C oracle and the fixtures produced by the reference's matcher.
+Index work: the bar is bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import linear_sum_assignment
+
+import relation_detr_b200 as rd
+from oracle import c_oracle
+from relation_detr_b200 import ops
+from test_lsap_oracle import _matrix, finish_like_reference
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _solve(mats):
+    pairs, status = ops.lsap_solve([torch.as_tensor(np.asarray(m, dtype=np.float32)).to(DEV) for m in mats])
+    torch.cuda.synchronize()
+    return [(r.cpu().numpy(), c.cpu().numpy()) for r, c in pairs], status.cpu().numpy()
+
+
+@pytest.mark.parametrize("kind", ["float", "small_int", "dup_cols", "dup_rows", "constant", "negative"])
+def test_solver_returns_scipys_pairs(kind):
+    rng = np.random.default_rng(sum(map(ord, kind)) + 1)
+    mats = [_matrix(kind, int(rng.integers(1, 70)), int(rng.integers(1, 70)), rng).astype(np.float32) for _ in range(150)]
+    got, status = _solve(mats)          # 150 problems: three launches of <= 64 CTAs
+    assert not status.any()
+    for m, (r, c) in zip(mats, got):
+        rr, cc = linear_sum_assignment(m)
+        assert np.array_equal(r, rr) and np.array_equal(c, cc), (kind, m.shape)
+
+
+def test_solver_matches_the_oracle_with_infinite_entries_and_reports_status():
+    rng = np.random.default_rng(11)
+    mats = [_matrix("with_inf", int(rng.integers(1, 30)), int(rng.integers(1, 30)), rng).astype(np.float32) for _ in range(120)]
+    nan = np.ones((5, 7), dtype=np.float32); nan[1, 2] = np.nan
+    ninf = np.ones((7, 5), dtype=np.float32); ninf[6, 4] = -np.inf
+    mats += [nan, ninf, np.full((3, 3), np.inf, dtype=np.float32)]
+    got, status = _solve(mats)
+    seen = set()
+    for m, (r, c), st in zip(mats, got, status):
+        try:
+            rr, cc = c_oracle.lsap(m)
+            assert st == 0 and np.array_equal(r, rr) and np.array_equal(c, cc)
+        except ValueError as e:
+            want = 1 if "infeasible" in str(e) else 2
+            assert st == want and (r == -1).all() and (c == -1).all()
+            seen.add(want)
+    assert seen == {1, 2}
+
+
+def test_solver_at_the_matchers_full_sizes():
+    """900 queries x crowded image, and the hybrid branch's 1500 queries x 6 copies of every target
+    (relation_detr.py:131-132): duplicated columns make the optimum non-unique, SciPy's choice must be kept."""
+    rng = np.random.default_rng(5)
+    mats = [rng.random((900, 100)).astype(np.float32), np.tile(rng.random((1500, 90)).astype(np.float32), (1, 6)),
+            rng.random((300, 300)).astype(np.float32), rng.random((60, 1500)).astype(np.float32)]
+    got, status = _solve(mats)
+    assert not status.any()
+    for m, (r, c) in zip(mats, got):
+        rr, cc = linear_sum_assignment(m)
+        assert np.array_equal(r, rr) and np.array_equal(c, cc), m.shape
+        assert len(np.unique(c)) == len(c)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "matcher_*.npz"))), ids=os.path.basename)
+def test_matcher_reproduces_the_reference_fixtures(path):
+    z = np.load(path)
+    mixed, gt_copy = bool(z["mixed"]), int(z["gt_copy"])
+    m = rd.HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2, mixed_match=mixed)
+    args = [torch.as_tensor(z[k]).to(DEV) for k in ("pred_boxes", "pred_logits", "gt_boxes", "gt_labels")]
+    # (1) the solver on the reference's own cost matrix: exact
+    cost = z["cost"]
+    gt_size = cost.shape[1]
+    if mixed:
+        k = min(int(cost.shape[0] * 0.5 / gt_size), gt_copy) if gt_size > 0 else gt_copy
+        cost = np.tile(cost, (1, k))
+    (pair,), status = _solve([cost])
+    src, tgt = finish_like_reference(pair[0], pair[1], gt_size, mixed)
+    assert status[0] == 0
+    if mixed:
+        assert np.array_equal(tgt, z["tgt_ind"])
+        assert sorted(zip(src.tolist(), tgt.tolist())) == sorted(zip(z["src_ind"].tolist(), z["tgt_ind"].tolist()))
+    else:
+        assert np.array_equal(src, z["src_ind"]) and np.array_equal(tgt, z["tgt_ind"])
+    # (2) the whole matcher, cost computed on the device as upstream does
+    s, t = m(*args, gt_copy=gt_copy)
+    assert s.is_cuda and s.dtype == torch.int64 and t.dtype == torch.int64
+    assert sorted(zip(s.tolist(), t.tolist())) == sorted(zip(z["src_ind"].tolist(), z["tgt_ind"].tolist()))
+    c_dev = m.calculate_cost(*args).cpu().numpy()
+    assert np.allclose(c_dev, z["cost"], rtol=1e-5, atol=1e-5)
+
+
+def test_match_batch_equals_per_image_calls_and_does_not_synchronise():
+    g = torch.Generator().manual_seed(3)
+    B, nq = 6, 900
+    pb = (torch.rand(B, nq, 4, generator=g) * 0.5 + 0.1).to(DEV)
+    pl = torch.randn(B, nq, 91, generator=g).to(DEV)
+    gts = [int(n) for n in (0, 1, 7, 23, 64, 5)]
+    gb = [(torch.rand(n, 4, generator=g) * 0.5 + 0.1).to(DEV) for n in gts]
+    gl = [torch.randint(0, 91, (n,), generator=g).to(DEV) for n in gts]
+    m = rd.HungarianMatcher(2, 5, 2)
+    one = list(map(m, pb, pl, gb, gl))                       # set_criterion.py:126
+    torch.cuda.synchronize()
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        torch.cuda.set_sync_debug_mode("warn")               # any implicit device->host sync is reported
+        try:
+            many = m.match_batch(pb, pl, gb, gl)
+        finally:
+            torch.cuda.set_sync_debug_mode("default")
+    assert not [str(w.message) for w in caught if "called a synchronizing" in str(w.message)]
+    for (s1, t1), (s2, t2), n in zip(one, many, gts):
+        assert len(s1) == n and torch.equal(s1, s2) and torch.equal(t1, t2)
+    for b, n in enumerate(gts):                              # against SciPy on the same device-computed cost
+        rr, cc = linear_sum_assignment(m.calculate_cost(pb[b], pl[b], gb[b], gl[b]).cpu().numpy())
+        assert np.array_equal(many[b][0].cpu().numpy(), rr) and np.array_equal(many[b][1].cpu().numpy(), cc)
+
+
+def test_errors_are_raised_not_swallowed():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.lsap_solve([torch.zeros(3, 3)])
+    with pytest.raises(RuntimeError, match="float32"):
+        ops.lsap_solve([torch.zeros(3, 3, dtype=torch.float64, device=DEV)])
+    with pytest.raises(RuntimeError, match="shared memory"):
+        ops.lsap_solve([torch.zeros(8000, 8000, device=DEV)])
+    m = rd.HungarianMatcher(1, 1, 1, check_status=True)
+    bad = torch.full((4, 4), float("nan"), device=DEV)
+    with pytest.raises(ValueError, match="invalid numeric"):
+        m._solve([bad])
