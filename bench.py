@@ -14,7 +14,7 @@ One JSON line on stdout (rank 0).  Keys beyond the base contract:
   roofline      dominant kernel (backward), algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
   e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
-  extra         the other measured variants (loc distributions, bf16, decoder shapes, relation op)
+  extra         the other measured variants (loc distributions, bf16, decoder shapes, relation op, one step of bipartite matching)
 """
 from __future__ import annotations
 
@@ -304,6 +304,41 @@ def measure_ceilings(torch, shape):
     return out
 
 
+def time_matching(torch, rd, steps, warmup, batch=2, gts=(7, 15)):
+    """One training step's bipartite matching: 14 prediction sets per image (7 x 900
+    queries, 7 x 1500 queries against 6 copies of every target).  Device solver timed with CUDA events; the
+    reference's way (``c.cpu()`` + SciPy, hungarian_matcher.py:80) timed on the same cost matrices."""
+    import time
+
+    from scipy.optimize import linear_sum_assignment
+    g = torch.Generator().manual_seed(0)
+    m = rd.HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2)
+    costs = []
+    for b in range(batch):
+        n = gts[b % len(gts)]
+        gb = torch.cat([torch.rand(n, 2, generator=g) * 0.8 + 0.1, torch.rand(n, 2, generator=g) * 0.3 + 0.02], -1).cuda()
+        gl = torch.randint(0, 91, (n,), generator=g).cuda()
+        for nq, rep in ((900, 1), (1500, 6)):
+            for _ in range(7):
+                pb = torch.cat([torch.rand(nq, 2, generator=g) * 0.8 + 0.1, torch.rand(nq, 2, generator=g) * 0.3 + 0.02], -1).cuda()
+                pl = (torch.randn(nq, 91, generator=g) * 2 - 2).cuda()
+                costs.append(m.calculate_cost(pb, pl, gb.repeat(rep, 1), gl.repeat(rep)).float())
+    for _ in range(warmup):
+        pairs, status = rd.ops.lsap_solve(costs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        pairs, status = rd.ops.lsap_solve(costs)
+    e1.record()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ref = [linear_sum_assignment(c.cpu()) for c in costs]
+    t_ref = (time.perf_counter() - t0) * 1e3
+    same = int(status.sum()) == 0 and all((p[0].cpu().numpy() == r[0]).all() and (p[1].cpu().numpy() == r[1]).all() for p, r in zip(pairs, ref))
+    return {"problems": len(costs), "device_solver_ms": round(e0.elapsed_time(e1) / steps, 4), "launches_per_call": 1,
+            "copy_to_host_plus_scipy_ms": round(t_ref, 3), "identical_to_scipy": bool(same)}
+
+
 def time_rel(torch, ops, wl, name, steps, warmup, fast):
     shape = wl.REL_SHAPES[name]
     r = wl.make_rel_inputs(shape, seed=0, device="cuda")
@@ -406,6 +441,7 @@ def run_ours(args):
         for name in ("rel_900_b8", "rel_1100_b8", "rel_2900_b1"):
             guarded(name + "_exact", lambda name=name: time_rel(torch, ops, workloads, name, k, w, False))
             guarded(name + "_fast", lambda name=name: time_rel(torch, ops, workloads, name, k, w, True))
+        guarded("matching_step_b2", lambda: time_matching(torch, rd, k, w))
     if rank == 0 and not args.no_cpu_baseline:
         gbs, cms, cores, sample = time_cpu_port(8, 2, 2, args.loc)  # ~10 s of host work on the GPU box
         cpu_baseline = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": round(cms, 2)}

@@ -189,6 +189,25 @@ int rdetr_lsap_solve(const float *const *cost, const int64_t *n_rows, const int6
                      void *workspace, size_t workspace_bytes, rdetr_stream_t stream);
 
 /*
+ * The matcher's cost matrices for a batch of problems in one launch (row N3, with rdetr_lsap_solve).
+ * Replaces HungarianMatcher.calculate_cost, models/matcher/hungarian_matcher.py:40-72 (about 30 eager
+ * kernels per problem): cost[q, g] = w_bbox * L1(pred_boxes[q], gt_boxes[g])
+ *                                  + w_class * (pos - neg)(sigmoid(pred_logits[q, gt_labels[g]]))
+ *                                  + w_giou * -GIoU(xyxy(pred_boxes[q]), xyxy(gt_boxes[g]))
+ * evaluated with the same single-precision operations in the same order as the eager chain, so the
+ * values are the same BITS (tests/test_lsap_gpu.py: torch.equal on the GPU) and the assignment that
+ * follows is the reference's.
+ *   pred_boxes[p] float32 [n_queries[p], 4] cxcywh (16-byte aligned), pred_logits[p] float32
+ *   [n_queries[p], num_classes], gt_boxes[p] float32 [n_gt[p], 4], gt_labels[p] int64 [n_gt[p]],
+ *   cost[p] float32 [n_queries[p], n_gt[p]] -- all device; the arrays of pointers / extents are HOST arrays.
+ */
+int rdetr_match_cost(const float *const *pred_boxes, const float *const *pred_logits,
+                     const float *const *gt_boxes, const int64_t *const *gt_labels, float *const *cost,
+                     const int64_t *n_queries, const int64_t *n_gt, int num_classes, float w_class,
+                     float w_bbox, float w_giou, double focal_alpha, double focal_gamma, int n_problems,
+                     rdetr_stream_t stream);
+
+/*
  * Diagnostics (not on the product path): measure on the current device the two hardware rates that
  * bound the MSDA kernels -- random 128-byte row gathers (8 lanes x 16-byte read-only loads per row) and
  * 128-byte vector reductions (red.global.add.v4.f32) -- over a caller-provided table of nrows rows.

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RDETR_OPS_LIB", os.path.join(PKG_DIR, "librdetr_ops.so"))
@@ -30,6 +30,7 @@ _SIGNATURES = {
     "rdetr_relation_backward": (c_int, [c_void_p] * 3 + [c_float, c_float] + [c_void_p] * 4 + [c_int] * 5 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_lsap_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_int]),
     "rdetr_lsap_solve": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_size_t, c_void_p]),
+    "rdetr_match_cost": (c_int, [c_void_p] * 7 + [c_int, c_float, c_float, c_float, c_double, c_double, c_int, c_void_p]),
     "rdetr_diag_gather_rows": (c_int, [c_void_p, c_longlong, c_int, c_void_p, ctypes.POINTER(c_longlong), c_void_p]),
     "rdetr_diag_red_rows": (c_int, [c_void_p, c_longlong, c_int, ctypes.POINTER(c_longlong), c_void_p]),
 }

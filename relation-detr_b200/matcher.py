@@ -1,11 +1,12 @@
 """Device-resident ``HungarianMatcher`` -- the reference's matcher without its host round trip.
 
 Mirrors ``models/matcher/hungarian_matcher.py`` of the reference (same constructor arguments, same
-``calculate_*`` methods, same ``forward`` signature and result order).  The cost matrix is computed by the
-same torch operations on the device, as upstream does; what changes is line 80 / 87: instead of
-``linear_sum_assignment(c.cpu())`` -- a device->host copy that stalls the stream once per image and per
-decoder layer -- the matrix is handed to ``rdetr_lsap_solve`` and the index tensors stay on the device.
-Results are the pairs SciPy returns for the same matrix, ties included (tests/test_lsap_gpu.py).
+``calculate_*`` methods, same ``forward`` signature and result order).  Two things change.  The cost matrix
+(upstream: ~30 eager kernels per problem, :40-72) comes from one ``rdetr_match_cost`` launch for all problems,
+which returns the eager chain's values bit for bit (``fused_cost=False`` keeps the eager chain).  And line
+80 / 87: instead of ``linear_sum_assignment(c.cpu())`` -- a device->host copy that stalls the stream once per
+image and per decoder layer -- the matrix is handed to ``rdetr_lsap_solve`` and the index tensors stay on the
+device.  Results are the pairs SciPy returns for the same matrix, ties included (tests/test_lsap_gpu.py).
 
 Differences, deliberate:
 * the two index tensors are CUDA int64 tensors (upstream: CPU tensors); every use in
@@ -53,7 +54,8 @@ class HungarianMatcher(nn.Module):
     """Drop-in for ``models.matcher.hungarian_matcher.HungarianMatcher`` (hungarian_matcher.py:8-91)."""
 
     def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha: float = 0.25,
-                 focal_gamma: float = 2.0, mixed_match: bool = False, check_status: bool = False):
+                 focal_gamma: float = 2.0, mixed_match: bool = False, check_status: bool = False,
+                 fused_cost: bool = True):
         super().__init__()
         self.cost_class = cost_class
         self.cost_bbox = cost_bbox
@@ -63,6 +65,7 @@ class HungarianMatcher(nn.Module):
         self.focal_gamma = focal_gamma
         self.mixed_match = mixed_match
         self.check_status = check_status
+        self.fused_cost = fused_cost
         self.last_status = None
 
     # -- cost terms: hungarian_matcher.py:40-72, same operations in the same order -----------------------
@@ -112,18 +115,24 @@ class HungarianMatcher(nn.Module):
                 raise ValueError("cost matrix is infeasible" if code == 1 else "matrix contains invalid numeric entries")
         return pairs
 
+    def _costs(self, pred_boxes, pred_logits, gt_boxes, gt_labels) -> List[Tensor]:
+        """Cost matrices of a batch of problems: one fused launch (``rdetr_match_cost``, the eager chain's
+        values bit for bit) or, with ``fused_cost=False``, ``calculate_cost`` per problem as upstream."""
+        if self.fused_cost:
+            return ops.match_cost([b.float() for b in pred_boxes], [l.float() for l in pred_logits], [b.float() for b in gt_boxes],
+                                  list(gt_labels), self.cost_class, self.cost_bbox, self.cost_giou, self.focal_alpha, self.focal_gamma)
+        return [self.calculate_cost(pb, pl, gb, gl) for pb, pl, gb, gl in zip(pred_boxes, pred_logits, gt_boxes, gt_labels)]
+
     @torch.no_grad()
     def forward(self, pred_boxes: Tensor, pred_logits: Tensor, gt_boxes: Tensor, gt_labels: Tensor, gt_copy: int = 1):
-        c, gt_size = self._prepare(self.calculate_cost(pred_boxes, pred_logits, gt_boxes, gt_labels), gt_copy)
-        (src_ind, tgt_ind), = self._solve([c])
-        return self._finish(src_ind, tgt_ind, gt_size)
+        return self.match_batch([pred_boxes], [pred_logits], [gt_boxes], [gt_labels], gt_copy)[0]
 
     @torch.no_grad()
     def match_batch(self, pred_boxes: Sequence[Tensor], pred_logits: Sequence[Tensor], gt_boxes: Sequence[Tensor],
                     gt_labels: Sequence[Tensor], gt_copy: int = 1) -> List[Tuple[Tensor, Tensor]]:
-        """All images of one prediction set in one solver launch; same result as
-        ``list(map(self, pred_boxes, pred_logits, gt_boxes, gt_labels))`` (set_criterion.py:126)."""
-        prepared = [self._prepare(self.calculate_cost(pb, pl, gb, gl), gt_copy)
-                    for pb, pl, gb, gl in zip(pred_boxes, pred_logits, gt_boxes, gt_labels)]
+        """Any number of (prediction set, image) problems in two launches (costs, assignment); same result as
+        ``list(map(self, pred_boxes, pred_logits, gt_boxes, gt_labels))`` (set_criterion.py:126).  The problems
+        need not share the number of queries, so the sets of several decoder layers can be matched together."""
+        prepared = [self._prepare(c, gt_copy) for c in self._costs(pred_boxes, pred_logits, gt_boxes, gt_labels)]
         pairs = self._solve([c for c, _ in prepared])
         return [self._finish(s, t, g) for (s, t), (_, g) in zip(pairs, prepared)]

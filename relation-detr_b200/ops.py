@@ -25,7 +25,7 @@ __all__ = [
     "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
     "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
-    "lsap_solve",
+    "lsap_solve", "match_cost",
 ]
 
 
@@ -400,3 +400,46 @@ def lsap_solve(costs: Sequence[Tensor]) -> Tuple[List[Tuple[Tensor, Tensor]], Te
     _lib.check(lib.rdetr_lsap_solve(cost_p, n_rows, n_cols, row_p, col_p, _ptr(status), P, _ptr(ws), ws_bytes, _stream(status)),
                "rdetr_lsap_solve")
     return out, status
+
+
+def match_cost(pred_boxes: Sequence[Tensor], pred_logits: Sequence[Tensor], gt_boxes: Sequence[Tensor],
+               gt_labels: Sequence[Tensor], cost_class: float, cost_bbox: float, cost_giou: float,
+               focal_alpha: float = 0.25, focal_gamma: float = 2.0) -> List[Tensor]:
+    """Cost matrices ``[n_queries, n_gt]`` of a batch of matching problems in one launch: the values (bit for
+    bit) that ``HungarianMatcher.calculate_cost`` of the reference computes with ~30 eager kernels per problem
+    (models/matcher/hungarian_matcher.py:40-72)."""
+    import ctypes
+
+    P = len(pred_boxes)
+    _require(P > 0 and len(pred_logits) == P and len(gt_boxes) == P and len(gt_labels) == P, "rdetr::match_cost: ragged argument lists")
+    dev = pred_boxes[0].device
+    num_classes = pred_logits[0].shape[-1]
+    keep, nq, ng = [], [], []
+    for pb, pl, gb, gl in zip(pred_boxes, pred_logits, gt_boxes, gt_labels):
+        for t in (pb, pl, gb, gl):
+            _require(t.is_cuda and t.device == dev, "rdetr::match_cost: tensors must be CUDA tensors on one device (no CPU path)")
+        _require(pb.dtype == torch.float32 and pl.dtype == torch.float32 and gb.dtype == torch.float32 and gl.dtype == torch.int64,
+                 "rdetr::match_cost: float32 boxes / logits and int64 labels expected")
+        _require(pb.dim() == 2 and pb.shape[1] == 4 and gb.dim() == 2 and gb.shape[1] == 4 and pl.dim() == 2
+                 and pl.shape[0] == pb.shape[0] and pl.shape[1] == num_classes and gl.shape == gb.shape[:1],
+                 f"rdetr::match_cost: shapes {tuple(pb.shape)} {tuple(pl.shape)} {tuple(gb.shape)} {tuple(gl.shape)}")
+        pb, gb = pb.detach().contiguous(), gb.detach().contiguous()
+        pb = pb if pb.data_ptr() % 16 == 0 else pb.clone()          # float4 loads
+        gb = gb if gb.data_ptr() % 16 == 0 else gb.clone()
+        keep.append((pb, pl.detach().contiguous(), gb, gl.contiguous()))
+        nq.append(pb.shape[0])
+        ng.append(gb.shape[0])
+    # one allocation for all matrices; every matrix starts on a 16-byte boundary
+    starts, cursor = [], 0
+    for a, b in zip(nq, ng):
+        starts.append(cursor)
+        cursor += (a * b + 3) // 4 * 4
+    flat = torch.empty(cursor, dtype=torch.float32, device=dev)
+    costs = [flat[s:s + a * b].view(a, b) for s, a, b in zip(starts, nq, ng)]
+    arr = lambda xs: (ctypes.c_void_p * P)(*xs)  # noqa: E731
+    _lib.check(_lib.lib().rdetr_match_cost(
+        arr([k[0].data_ptr() for k in keep]), arr([k[1].data_ptr() for k in keep]), arr([k[2].data_ptr() for k in keep]),
+        arr([k[3].data_ptr() for k in keep]), arr([c.data_ptr() for c in costs]), (ctypes.c_int64 * P)(*nq), (ctypes.c_int64 * P)(*ng),
+        num_classes, float(cost_class), float(cost_bbox), float(cost_giou), float(focal_alpha), float(focal_gamma), P, _stream(flat)),
+        "rdetr_match_cost")
+    return costs

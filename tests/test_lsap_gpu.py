@@ -97,6 +97,41 @@ def test_matcher_reproduces_the_reference_fixtures(path):
     assert np.allclose(c_dev, z["cost"], rtol=1e-5, atol=1e-5)
 
 
+def _ulps(a, b):
+    ia, ib = a.contiguous().view(torch.int32).long(), b.contiguous().view(torch.int32).long()
+    return int((ia - ib).abs().max()) if a.numel() else 0
+
+
+def test_fused_cost_kernel_returns_the_eager_chains_bits():
+    """rdetr_match_cost against HungarianMatcher.calculate_cost evaluated by eager torch on the same device
+    (the reference's way, hungarian_matcher.py:40-72).  The assignment that follows must be the reference's,
+    so the bar is equality of the float32 bit patterns, not a tolerance."""
+    g = torch.Generator().manual_seed(9)
+    eager = rd.HungarianMatcher(2, 5, 2, fused_cost=False)
+    sets = []
+    for nq, ng, ncls in ((900, 37, 91), (1500, 6 * 15, 91), (300, 1, 91), (50, 0, 91), (20, 64, 20), (7, 3, 2)):
+        pb = torch.cat([torch.rand(nq, 2, generator=g) * 0.8 + 0.1, torch.rand(nq, 2, generator=g) * 0.3 + 0.02], -1).to(DEV)
+        pl = (torch.randn(nq, ncls, generator=g) * 3 - 2).to(DEV)
+        gb = torch.cat([torch.rand(ng, 2, generator=g) * 0.8 + 0.1, torch.rand(ng, 2, generator=g) * 0.3 + 0.02], -1).to(DEV)
+        gl = torch.randint(0, ncls, (ng,), generator=g).to(DEV)
+        sets.append((pb, pl, gb, gl))
+    for ncls in (91, 20, 2):
+        group = [s for s in sets if s[1].shape[1] == ncls]
+        fused = ops.match_cost(*zip(*group), 2, 5, 2, 0.25, 2.0)
+        for (pb, pl, gb, gl), c in zip(group, fused):
+            want = eager.calculate_cost(pb, pl, gb, gl)
+            assert c.shape == want.shape
+            assert torch.equal(c, want), f"{tuple(c.shape)}: differs by up to {_ulps(c, want)} ulp, max abs {float((c - want).abs().max()):.3e}"
+    # extreme logits (saturated sigmoid) and degenerate boxes keep the same bits too
+    pb = torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.1, 0.9, 1e-4, 0.3], [0.5, 0.5, 1.0, 1.0]], device=DEV)
+    pl = torch.tensor([[40.0, -40.0, 0.0], [-100.0, 100.0, 1e-3], [15.9, -15.9, 7.0]], device=DEV)
+    gb = torch.tensor([[0.5, 0.5, 0.2, 0.2], [0.9, 0.1, 0.05, 0.05]], device=DEV)
+    gl = torch.tensor([0, 1], device=DEV)
+    (c,) = ops.match_cost([pb], [pl], [gb], [gl], 2, 5, 2, 0.25, 2.0)
+    want = eager.calculate_cost(pb, pl, gb, gl)
+    assert torch.equal(c, want), f"differs by up to {_ulps(c, want)} ulp"
+
+
 def test_match_batch_equals_per_image_calls_and_does_not_synchronise():
     g = torch.Generator().manual_seed(3)
     B, nq = 6, 900
