@@ -11,7 +11,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import modules, ops
+from . import matcher, modules, ops
 
 # modules of the reference that bind the two classes by name at import time
 _MSDA_USERS = (
@@ -24,8 +24,14 @@ _MSDA_USERS = (
 )
 
 
-def install(reference_root: str | None = None, strict: bool = False) -> list:
-    """Returns the list of ``module.attribute`` names that were rebound."""
+# modules of the reference that bind HungarianMatcher by name (the configs import it from the first one)
+_MATCHER_USERS = ("models.matcher.hungarian_matcher",)
+
+
+def install(reference_root: str | None = None, strict: bool = False, matcher_too: bool = True) -> list:
+    """Returns the list of ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
+    ``HungarianMatcher`` (device-resident matching): its index tensors are CUDA
+    tensors, which every use in ``models/bricks/set_criterion.py`` accepts."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     rebound = []
@@ -42,4 +48,13 @@ def install(reference_root: str | None = None, strict: bool = False) -> list:
             if hasattr(mod, attr):
                 setattr(mod, attr, repl)
                 rebound.append(f"{name}.{attr}")
+    for name in _MATCHER_USERS if matcher_too else ():
+        try:
+            mod = importlib.import_module(name)
+        except Exception:
+            if strict:
+                raise
+            continue
+        mod.HungarianMatcher = matcher.HungarianMatcher
+        rebound.append(f"{name}.HungarianMatcher")
     return rebound
