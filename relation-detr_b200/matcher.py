@@ -136,3 +136,45 @@ class HungarianMatcher(nn.Module):
         prepared = [self._prepare(c, gt_copy) for c in self._costs(pred_boxes, pred_logits, gt_boxes, gt_labels)]
         pairs = self._solve([c for c, _ in prepared])
         return [self._finish(s, t, g) for (s, t), (_, g) in zip(pairs, prepared)]
+
+
+@torch.no_grad()
+def match_prediction_sets(matcher: HungarianMatcher, outputs: dict, targets: Sequence[dict],
+                          two_stage_binary_cls: bool = False) -> dict:
+    """Match every prediction set of one criterion call -- the final layer, each ``aux_outputs[i]`` and
+    ``enc_outputs`` -- against the images' targets with ONE cost launch and ONE solver launch.
+
+    ``SetCriterion.forward`` of the reference (models/bricks/set_criterion.py:133-171) walks these sets one
+    after the other and matches inside ``calculate_loss`` (:123-126), which already accepts precomputed
+    ``indices``.  -> ``{"main": [...], "aux": [[...], ...], "enc": [...]}``, each list holding one
+    ``(src_ind, tgt_ind)`` per image, ready to be passed as that argument.  ``two_stage_binary_cls`` zeroes the
+    labels for the encoder set (:165-167)."""
+    gt_boxes = [t["boxes"] for t in targets]
+    gt_labels = [t["labels"] for t in targets]
+    sets = [("main", outputs["pred_boxes"], outputs["pred_logits"], gt_labels)]
+    for aux in outputs.get("aux_outputs", ()):
+        sets.append(("aux", aux["pred_boxes"], aux["pred_logits"], gt_labels))
+    if "enc_outputs" in outputs:
+        enc = outputs["enc_outputs"]
+        enc_labels = [torch.zeros_like(l) for l in gt_labels] if two_stage_binary_cls else gt_labels
+        sets.append(("enc", enc["pred_boxes"], enc["pred_logits"], enc_labels))
+    # the fused cost kernel takes one class count per launch: group the sets by it (binary encoder heads differ)
+    result = {"main": None, "aux": [], "enc": None}
+    by_classes = {}
+    for entry in sets:
+        by_classes.setdefault(entry[2].shape[-1], []).append(entry)
+    solved = {}
+    for group in by_classes.values():
+        pb, pl, gb, gl = [], [], [], []
+        for _, boxes, logits, labels in group:
+            pb += list(boxes); pl += list(logits); gb += gt_boxes; gl += labels
+        pairs = matcher.match_batch(pb, pl, gb, gl)
+        n = len(targets)
+        for k, entry in enumerate(group):
+            solved[id(entry)] = pairs[k * n:(k + 1) * n]
+    for entry in sets:
+        if entry[0] == "aux":
+            result["aux"].append(solved[id(entry)])
+        else:
+            result[entry[0]] = solved[id(entry)]
+    return result

@@ -15,6 +15,7 @@ void rdetr_oracle_msda_forward_f64(const double *, const int64_t *, const int64_
                                    int, int, int, int, int, int);
 void rdetr_oracle_msda_backward_f64(const double *, const int64_t *, const int64_t *, const double *, const double *,
                                     const double *, double *, double *, double *, int, int, int, int, int, int, int);
+int rdetr_oracle_lsap(const double *, int64_t, int64_t, int64_t *, int64_t *);
 void rdetr_oracle_rel_forward_f64(const double *, const double *, const double *, const double *, const double *, double, double,
                                   const uint8_t *, double *, int, int, int, int, int);
 }
@@ -115,6 +116,37 @@ int main()
         printf("relation (%s): out %.2e\n", flags ? "FAST" : "EXACT", e);
         if (!(e <= 1e-4)) return 5;
         if (ws) cudaFree(ws);
+    }
+    // ---- assignment: two problems (one per orientation), duplicated columns so that ties must be broken SciPy's way
+    {
+        const int64_t rows[2] = {40, 6}, cols[2] = {9, 15};
+        std::vector<float> c0(40 * 9), c1(6 * 15);
+        for (int i = 0; i < 40; ++i) for (int j = 0; j < 9; ++j) c0[i * 9 + j] = (float)(((i * 7 + (j % 3) * 13) % 11) * 0.25);
+        for (size_t i = 0; i < c1.size(); ++i) c1[i] = (float)((i * 2654435761u >> 7) % 5);
+        float *d_c0 = to_dev(c0), *d_c1 = to_dev(c1);
+        int64_t *d_idx;
+        int32_t *d_status;
+        CK(cudaMalloc(&d_idx, (9 + 9 + 6 + 6) * sizeof(int64_t)));
+        CK(cudaMalloc(&d_status, 2 * sizeof(int32_t)));
+        const float *cost[2] = {d_c0, d_c1};
+        int64_t *ri[2] = {d_idx, d_idx + 18}, *ci[2] = {d_idx + 9, d_idx + 24};
+        const size_t wsb = rdetr_lsap_workspace_bytes(rows, cols, 2);
+        void *ws = nullptr;
+        if (wsb) CK(cudaMalloc(&ws, wsb));
+        RK(rdetr_lsap_solve(cost, rows, cols, ri, ci, d_status, 2, ws, wsb, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<int64_t> idx(30);
+        int32_t status[2];
+        CK(cudaMemcpy(idx.data(), d_idx, idx.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(status, d_status, sizeof(status), cudaMemcpyDeviceToHost));
+        std::vector<double> c0d(c0.begin(), c0.end()), c1d(c1.begin(), c1.end());
+        int64_t r0[9], k0[9], r1[6], k1[6];
+        if (rdetr_oracle_lsap(c0d.data(), 40, 9, r0, k0) != 0 || rdetr_oracle_lsap(c1d.data(), 6, 15, r1, k1) != 0) return 8;
+        if (status[0] != 0 || status[1] != 0) return 8;
+        for (int k = 0; k < 9; ++k) if (idx[k] != r0[k] || idx[9 + k] != k0[k]) { printf("lsap problem 0 differs at %d\n", k); return 8; }
+        for (int k = 0; k < 6; ++k) if (idx[18 + k] != r1[k] || idx[24 + k] != k1[k]) { printf("lsap problem 1 differs at %d\n", k); return 8; }
+        printf("lsap: 2 problems identical to the oracle\n");
+        if (rdetr_lsap_solve(cost, rows, cols, ri, ci, d_status, 2, nullptr, 0, st) != RDETR_ERR_WORKSPACE) return 9;
     }
     // error behaviour: unsupported head dim, host pointer
     if (rdetr_msda_forward(d_value, d_shapes, d_lsi, d_loc, d_attn, d_out, B, S, M, 16, L, Nq, P, RDETR_DTYPE_F32, st) != RDETR_ERR_UNSUPPORTED) return 6;

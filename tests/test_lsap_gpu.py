@@ -159,6 +159,36 @@ def test_match_batch_equals_per_image_calls_and_does_not_synchronise():
         assert np.array_equal(many[b][0].cpu().numpy(), rr) and np.array_equal(many[b][1].cpu().numpy(), cc)
 
 
+def test_all_prediction_sets_of_a_criterion_call_in_one_go():
+    """match_prediction_sets == the reference's walk over main / aux / enc outputs (set_criterion.py:133-171)."""
+    from relation_detr_b200.matcher import match_prediction_sets
+    g = torch.Generator().manual_seed(21)
+    B, nq, ncls = 2, 300, 91
+    mk = lambda: {"pred_boxes": (torch.rand(B, nq, 4, generator=g) * 0.5 + 0.1).to(DEV),  # noqa: E731
+                  "pred_logits": torch.randn(B, nq, ncls, generator=g).to(DEV)}
+    outputs = mk()
+    outputs["aux_outputs"] = [mk() for _ in range(5)]
+    outputs["enc_outputs"] = mk()
+    targets = [{"boxes": (torch.rand(n, 4, generator=g) * 0.5 + 0.1).to(DEV), "labels": torch.randint(0, ncls, (n,), generator=g).to(DEV)}
+               for n in (9, 0)]
+    m = rd.HungarianMatcher(2, 5, 2)
+    got = match_prediction_sets(m, outputs, targets, two_stage_binary_cls=True)
+
+    def walk(o, labels):
+        out = []
+        for b in range(B):
+            c = m.calculate_cost(o["pred_boxes"][b], o["pred_logits"][b], targets[b]["boxes"], labels[b]).cpu().numpy()
+            out.append(linear_sum_assignment(c))
+        return out
+
+    labels = [t["labels"] for t in targets]
+    for want, have in ((walk(outputs, labels), got["main"]), (walk(outputs["enc_outputs"], [torch.zeros_like(l) for l in labels]), got["enc"]),
+                       *((walk(a, labels), h) for a, h in zip(outputs["aux_outputs"], got["aux"]))):
+        for (r, c), (s, t) in zip(want, have):
+            assert np.array_equal(r, s.cpu().numpy()) and np.array_equal(c, t.cpu().numpy())
+    assert len(got["aux"]) == 5
+
+
 def test_errors_are_raised_not_swallowed():
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.lsap_solve([torch.zeros(3, 3)])
