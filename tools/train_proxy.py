@@ -85,7 +85,36 @@ class TransformerProxy(nn.Module):
         c1, b1 = self.decoder(main["query"], main["reference_points"], x, ss, lsi, main["valid_ratios"], main["attn_mask"])
         c2, b2 = self.decoder(hybrid["query"], hybrid["reference_points"], x, ss, lsi, hybrid["valid_ratios"], None,
                                      skip_relation=True)
-        return c1.square().mean() + b1.square().mean() + c2.square().mean() + b2.square().mean()
+        loss = c1.square().mean() + b1.square().mean() + c2.square().mean() + b2.square().mean()
+        return loss, c1, b1, c2, b2
+
+
+def matched_box_loss(how, matcher, c1, b1, c2, b2, gts, n_dn, hybrid_assign=6):
+    """Bipartite matching of every decoder layer's predictions (main pass: the 900 matching queries after the
+    denoising rows; hybrid pass: 1500 queries against ``hybrid_assign`` copies of the targets,
+    relation_detr.py:96-134) followed by an L1 loss on the matched boxes.  ``how`` = "device": this repository's
+    matcher, all problems in two launches, no synchronisation; "scipy": the reference's way, per problem
+    eager cost -> ``.cpu()`` -> SciPy (hungarian_matcher.py:74-81)."""
+    from scipy.optimize import linear_sum_assignment
+
+    B = c1.shape[1]
+    problems = []  # (pred_boxes with grad, detached boxes, logits, gt boxes, gt labels)
+    for c, b, skip, rep in ((c1, b1, n_dn, 1), (c2, b2, 0, hybrid_assign)):
+        for layer in range(c.shape[0]):
+            for i in range(B):
+                problems.append((b[layer, i, skip:], b[layer, i, skip:].detach().float(), c[layer, i, skip:].detach().float(),
+                                 gts[i][0].repeat(rep, 1), gts[i][1].repeat(rep)))
+    if how == "device":
+        pairs = matcher.match_batch(*[[p[k] for p in problems] for k in (1, 2, 3, 4)])
+    else:
+        pairs = []
+        for _, pb, pl, gb, gl in problems:
+            r, c_ = linear_sum_assignment(matcher.calculate_cost(pb, pl, gb, gl).cpu())
+            pairs.append((torch.as_tensor(r), torch.as_tensor(c_)))
+    loss = 0.0
+    for (pred, _, _, gb, _), (src, tgt) in zip(problems, pairs):
+        loss = loss + (pred[src].float() - gb[tgt]).abs().sum()
+    return loss / max(1, sum(len(p[3]) for p in problems))
 
 
 def main():
@@ -97,7 +126,12 @@ def main():
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--backbone", action="store_true", help="prepend ResNet-50 + channel mapper on 800x1344 images")
     ap.add_argument("--graph", action="store_true", help="capture the whole step (fwd+bwd+clip+AdamW) in one CUDA graph")
+    ap.add_argument("--matching", choices=("none", "device", "scipy"), default="none",
+                    help="add per-layer bipartite matching + matched box loss: this repository's device matcher, or the "
+                         "reference's cost -> .cpu() -> SciPy")
+    ap.add_argument("--gt", type=int, nargs="*", default=[7, 15], help="ground-truth boxes per image (cycled)")
     args = ap.parse_args()
+    assert not (args.graph and args.matching != "none"), "--graph is measured without matching"
     rank, local_rank, world = rdist.env_rank_world()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -120,10 +154,19 @@ def main():
     main_in = dh.make_inputs(args.batch, 900, 200, levels, seed=rank, device=dev)
     hyb_in = dh.make_inputs(args.batch, 1500, 0, levels, seed=50 + rank, device=dev)
 
+    gts = []
+    for i in range(args.batch):
+        n = args.gt[i % len(args.gt)]
+        gts.append((torch.cat([torch.rand((n, 2), device=dev, generator=g) * 0.8 + 0.1, torch.rand((n, 2), device=dev, generator=g) * 0.3 + 0.02], -1),
+                    torch.randint(0, 91, (n,), device=dev, generator=g)))
+    matcher = rd.HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2, fused_cost=args.matching == "device")
+
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
-            loss = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)
+            loss, c1, b1, c2, b2 = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)
+        if args.matching != "none":
+            loss = loss + matched_box_loss(args.matching, matcher, c1, b1, c2, b2, gts, 200)
         loss.backward()
         torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
         opt.step()
@@ -143,7 +186,7 @@ def main():
         opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.bf16):
-                static_loss = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)
+                static_loss = ddp(feats, pos, ref2d, ss, lsi, main_in, hyb_in)[0]
             static_loss.backward()
             torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
             opt.step()
@@ -168,7 +211,7 @@ def main():
         print(json.dumps({"workload": ("train_proxy: " + ("ResNet-50 + channel mapper (800x1344 images) + " if args.backbone else "")
                                        + "6-layer deformable encoder + relation decoder (main + hybrid), fwd+bwd+AdamW, DDP/NCCL"),
                           "n_gpus": world, "batch_per_gpu": args.batch, "precision": "bf16 autocast" if args.bf16 else ("tf32 matmul" if args.tf32 else "fp32"),
-                          "cuda_graph": bool(args.graph), "params_M": round(nparams / 1e6, 2), "ms_per_step": round(ms, 3),
+                          "cuda_graph": bool(args.graph), "matching": args.matching, "params_M": round(nparams / 1e6, 2), "ms_per_step": round(ms, 3),
                           "imgs_per_s": round(world * args.batch / ms * 1e3, 2), "loss": float(loss.detach())}))
     if world > 1:
         torch.distributed.destroy_process_group()
