@@ -1,9 +1,11 @@
 """relation-detr_b200: B200-native (sm_100a) replacement for the Relation-DETR hot path.
 
-Two operators behind the reference's own module API:
+Behind the reference's own module API:
 
 * ``MultiScaleDeformableAttention`` forward/backward  (reference: models/bricks/ms_deform_attn.py)
 * ``PositionRelationEmbedding``                        (reference: models/bricks/relation_transformer.py:481-532)
+* ``HungarianMatcher`` (row N3): cost matrices + assignment on the device, SciPy-identical pairs
+                                                        (reference: models/matcher/hungarian_matcher.py)
 
 The kernels live in ``csrc/`` and are reached through the C-ABI library ``librdetr_ops.so``
 (declared in ``include/rdetr_ops.h``).  There is no CPU fallback: calling an operator without the

@@ -247,12 +247,6 @@ extern "C" int rdetr_lsap_solve(const float *const *cost, const int64_t *n_rows,
     if (n_problems == 0) return RDETR_OK;
     if (!cost || !n_rows || !n_cols || !row_ind || !col_ind || !status)
         return fail(RDETR_ERR_INVALID_ARGUMENT, "lsap: null argument");
-    DeviceGuard guard(status);
-    if (guard.status() != RDETR_OK) return guard.status();
-    if (workspace_bytes < rdetr_lsap_workspace_bytes(n_rows, n_cols, n_problems))
-        return fail(RDETR_ERR_WORKSPACE, "lsap: workspace of %zu bytes, %zu needed (rdetr_lsap_workspace_bytes)", workspace_bytes,
-                    rdetr_lsap_workspace_bytes(n_rows, n_cols, n_problems));
-    if (workspace_bytes > 0 && !workspace) return fail(RDETR_ERR_INVALID_ARGUMENT, "lsap: null workspace");
 
     size_t smem_max = 0;
     for (int p = 0; p < n_problems; ++p) {
@@ -267,6 +261,12 @@ extern "C" int rdetr_lsap_solve(const float *const *cost, const int64_t *n_rows,
         const size_t s = lsap_smem_bytes((int)nr, (int)nc);
         if (s > smem_max) smem_max = s;
     }
+    if (workspace_bytes < rdetr_lsap_workspace_bytes(n_rows, n_cols, n_problems))
+        return fail(RDETR_ERR_WORKSPACE, "lsap: workspace of %zu bytes, %zu needed (rdetr_lsap_workspace_bytes)", workspace_bytes,
+                    rdetr_lsap_workspace_bytes(n_rows, n_cols, n_problems));
+    if (workspace_bytes > 0 && !workspace) return fail(RDETR_ERR_INVALID_ARGUMENT, "lsap: null workspace");
+    const DeviceGuard guard(status);
+    if (guard.status() != RDETR_OK) return guard.status();
     static thread_local int configured_device = -1;
     int dev = 0;
     int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");

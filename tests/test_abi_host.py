@@ -57,6 +57,19 @@ def test_abi_rejects_bad_arguments_without_a_gpu():
     assert L.rdetr_msda_backward_workspace_bytes(2, 10, 8, 32, 1, 1, 4, 1) == 2 * 10 * 8 * 32 * 4
     assert L.rdetr_msda_backward_workspace_bytes(2, 10, 8, 32, 1, 1, 4, 0) == 0
     assert L.rdetr_relation_workspace_bytes(2, 10, 6, 1) == 2 * 16 * 36 * 4 and L.rdetr_relation_workspace_bytes(2, 10, 6, 0) == 0
+    # assignment solver / cost kernel: extents are validated before anything touches a device
+    import ctypes
+    one = lambda v: (ctypes.c_int64 * 1)(v)  # noqa: E731
+    ptr = (ctypes.c_void_p * 1)(16)
+    assert L.rdetr_lsap_workspace_bytes(one(900), one(40), 1) == (900 * 40 * 4 + 255) // 256 * 256
+    assert L.rdetr_lsap_workspace_bytes(one(40), one(900), 1) == 0
+    assert L.rdetr_lsap_solve(ptr, one(3), one(3), ptr, ptr, 16, -1, None, 0, None) == 1
+    assert L.rdetr_lsap_solve(ptr, one(3), one(3), ptr, ptr, 16, 0, None, 0, None) == 0
+    assert L.rdetr_lsap_solve(ptr, one(-3), one(3), ptr, ptr, 16, 1, None, 0, None) == 1
+    assert L.rdetr_lsap_solve(None, one(3), one(3), ptr, ptr, 16, 1, None, 0, None) == 1 and b"null" in L.rdetr_last_error()
+    assert L.rdetr_match_cost(ptr, ptr, ptr, ptr, ptr, one(3), one(3), 0, 1.0, 1.0, 1.0, 0.25, 2.0, 1, None) == 1
+    assert L.rdetr_match_cost(ptr, ptr, ptr, ptr, ptr, one(0), one(3), 91, 1.0, 1.0, 1.0, 0.25, 2.0, 1, None) == 0   # nothing to do
+    assert L.rdetr_match_cost(ptr, ptr, ptr, ptr, ptr, one(1 << 20), one(1 << 20), 91, 1.0, 1.0, 1.0, 0.25, 2.0, 1, None) == 1
     with pytest.raises(_lib.RdetrOpsError):
         _lib.check(2, "x")
 
@@ -154,11 +167,22 @@ def test_install_rebinds_reference_names():
     ref_import.load()
     import models.bricks.ms_deform_attn as ref_msda
     import models.bricks.relation_transformer as ref_rt
+    import models.matcher.hungarian_matcher as ref_matcher
     saved = (ref_msda.MultiScaleDeformableAttention, ref_msda.MultiScaleDeformableAttnFunction,
              ref_rt.MultiScaleDeformableAttention, ref_rt.PositionRelationEmbedding)
+    saved_matcher = ref_matcher.HungarianMatcher
     try:
+        assert "models.matcher.hungarian_matcher.HungarianMatcher" not in install.install(matcher_too=False)
+        assert ref_matcher.HungarianMatcher is saved_matcher
         rebound = install.install()
         assert "models.bricks.relation_transformer.PositionRelationEmbedding" in rebound
+        assert "models.matcher.hungarian_matcher.HungarianMatcher" in rebound
+        assert ref_matcher.HungarianMatcher is rd.HungarianMatcher
+        import inspect
+        want = inspect.signature(saved_matcher.__init__).parameters
+        have = inspect.signature(rd.HungarianMatcher.__init__).parameters
+        assert list(want) == list(have)[:len(want)] and all(want[k].default == have[k].default for k in want)
+        assert list(inspect.signature(saved_matcher.forward).parameters) == list(inspect.signature(rd.HungarianMatcher.forward).parameters)
         assert ref_rt.MultiScaleDeformableAttention is rd.MultiScaleDeformableAttention
         layer = ref_rt.RelationTransformerEncoderLayer(256, 1024, 0.0, 8, torch.nn.ReLU(), 4, 4) \
             if hasattr(ref_rt, "RelationTransformerEncoderLayer") else None
@@ -167,6 +191,7 @@ def test_install_rebinds_reference_names():
     finally:
         (ref_msda.MultiScaleDeformableAttention, ref_msda.MultiScaleDeformableAttnFunction,
          ref_rt.MultiScaleDeformableAttention, ref_rt.PositionRelationEmbedding) = saved
+        ref_matcher.HungarianMatcher = saved_matcher
 
 
 def test_shard_range_tiles_exactly():
