@@ -25,8 +25,12 @@
 
 namespace rdetr {
 
+// 256 threads, 8 columns per thread and batch.  A 1024-thread x 2-column shape was measured and dropped: 0.636 vs
+// 0.630 ms on one step's problems, 5.46 vs 5.43 ms with crowded images (profiles/r01_tune_lsap.txt) -- a search step costs
+// one cost-row round trip plus the reduction whatever the thread count.
 constexpr int kLsapThreads = 256;
 constexpr int kLsapWarps = kLsapThreads / 32;
+constexpr int kLsapBatch = 8;
 constexpr int kLsapTasksPerLaunch = 64;          // 48-byte descriptors: 3 KB of the 4 KB kernel-parameter space
 constexpr size_t kLsapMaxSmem = 200 * 1024;
 
@@ -105,6 +109,7 @@ lsap_kernel(const __grid_constant__ LsapLaunch launch)
     const unsigned total = (unsigned)nr * (unsigned)nc;
     bool bad = false;
     if (transposed) {
+#pragma unroll 8
         for (unsigned e = tid; e < total; e += kLsapThreads) {
             const float x = __ldg(task.cost + e);
             bad |= (x != x) || (x == -INFINITY);
@@ -112,6 +117,7 @@ lsap_kernel(const __grid_constant__ LsapLaunch launch)
             task.scratch[(size_t)g * nc + q] = x;
         }
     } else {
+#pragma unroll 8
         for (unsigned e = tid; e < total; e += kLsapThreads) {
             const float x = __ldg(task.cost + e);
             bad |= (x != x) || (x == -INFINITY);
@@ -140,14 +146,34 @@ lsap_kernel(const __grid_constant__ LsapLaunch launch)
             unsigned long long key = ~0ULL;          // loses against every real column (+inf included)
             unsigned code = 0;
             int col = -1;
-            for (int t = tid; t < n_todo; t += kLsapThreads) {
-                const int j = todo[t];
-                const double r = ((min_val + (double)crow[j]) - u_i) - v[j];
-                double d = dist[j];
-                if (r < d) { path[j] = i; dist[j] = r; d = r; }
-                const unsigned long long k = order_key(d);
-                const unsigned cd = row4col[j] < 0 ? (0x80000000u | (unsigned)t) : (0x7fffffffu - (unsigned)t);
-                if (k < key || (k == key && cd > code)) { key = k; code = cd; col = j; }
+            // kLsapBatch columns per thread at a time: all loads of a batch are issued before its first store, so
+            // the cost-row reads (L1/L2 latency) of a thread overlap instead of queueing behind `dist[j] = r`
+            // (the compiler cannot prove that two slots name different columns; the algorithm guarantees it)
+            for (int base = tid; base < n_todo; base += kLsapThreads * kLsapBatch) {
+                int jj[kLsapBatch], owner[kLsapBatch];
+                float cc[kLsapBatch];
+                double vv[kLsapBatch], dd[kLsapBatch];
+#pragma unroll
+                for (int k = 0; k < kLsapBatch; ++k) {
+                    const int t = base + k * kLsapThreads;
+                    jj[k] = t < n_todo ? todo[t] : -1;
+                }
+#pragma unroll
+                for (int k = 0; k < kLsapBatch; ++k) {
+                    const int j = jj[k] < 0 ? 0 : jj[k];
+                    cc[k] = crow[j]; vv[k] = v[j]; dd[k] = dist[j]; owner[k] = row4col[j];
+                }
+#pragma unroll
+                for (int k = 0; k < kLsapBatch; ++k) {
+                    if (jj[k] < 0) continue;
+                    const int t = base + k * kLsapThreads, j = jj[k];
+                    const double r = ((min_val + (double)cc[k]) - u_i) - vv[k];
+                    double d = dd[k];
+                    if (r < d) { path[j] = i; dist[j] = r; d = r; }
+                    const unsigned long long kk = order_key(d);
+                    const unsigned cd = owner[k] < 0 ? (0x80000000u | (unsigned)t) : (0x7fffffffu - (unsigned)t);
+                    if (kk < key || (kk == key && cd > code)) { key = kk; code = cd; col = j; }
+                }
             }
             const unsigned my_code = code;
             const unsigned long long my_key = key;
