@@ -102,3 +102,31 @@ def test_oracle_reproduces_the_reference_matcher(path):
         assert sorted(zip(src.tolist(), tgt.tolist())) == sorted(zip(z["src_ind"].tolist(), z["tgt_ind"].tolist()))
     else:
         assert np.array_equal(src, z["src_ind"]) and np.array_equal(tgt, z["tgt_ind"])
+
+
+def test_oracle_is_optimal_against_brute_force():
+    """Independent of SciPy: on small matrices the oracle's total cost equals the minimum over all assignments."""
+    import itertools
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        nr, nc = int(rng.integers(1, 6)), int(rng.integers(1, 7))
+        c = rng.integers(-5, 6, (nr, nc)).astype(np.float64) if rng.random() < 0.5 else rng.standard_normal((nr, nc))
+        r, k = c_oracle.lsap(c)
+        assert len(r) == min(nr, nc) and len(set(r.tolist())) == len(r) and len(set(k.tolist())) == len(k)
+        if nr <= nc:
+            best = min(sum(c[i, p[i]] for i in range(nr)) for p in itertools.permutations(range(nc), nr))
+        else:
+            best = min(sum(c[p[j], j] for j in range(nc)) for p in itertools.permutations(range(nr), nc))
+        assert abs(c[r, k].sum() - best) <= 1e-12 * max(1.0, abs(best))
+
+
+def test_eager_cost_terms_reproduce_the_reference_fixtures():
+    """relation-detr_b200/matcher.py restates torchvision's box conversion and GIoU so that the package does not
+    import torchvision; on the CPU its calculate_cost must give the bits the reference's matcher stored."""
+    import torch
+    import relation_detr_b200 as rd
+    m = rd.HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2, fused_cost=False)
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "matcher_*.npz"))):
+        z = np.load(path)
+        c = m.calculate_cost(*[torch.as_tensor(z[k]) for k in ("pred_boxes", "pred_logits", "gt_boxes", "gt_labels")])
+        assert np.array_equal(c.numpy(), z["cost"]), os.path.basename(path)
