@@ -15,6 +15,9 @@ Differences, deliberate:
 * SciPy's ``ValueError`` for an infeasible matrix / a NaN entry cannot be raised without synchronising.
   ``check_status=True`` restores it (one sync per call); by default the solver's status word stays on the
   device in ``last_status`` and failed problems return ``-1`` indices;
+* the fused cost kernel computes in float32 and up-casts bf16/fp16 predictions first; under autocast the reference
+  evaluates the class term in the logits' reduced precision.  ``fused_cost=False`` keeps the eager chain and with it
+  the reference's dtype behaviour (the solver takes the float32 image of whatever that chain produced, exactly);
 * ``match_batch`` solves all images of one prediction set in a single launch (upstream: ``map`` over images).
 """
 from __future__ import annotations
