@@ -73,23 +73,26 @@ class HungarianMatcher(nn.Module):
 
     # -- cost terms: hungarian_matcher.py:40-72, same operations in the same order -----------------------
     def calculate_class_cost(self, pred_logits, gt_labels, **kwargs):
-        out_prob = pred_logits.sigmoid()
-        neg_cost_class = -(1 - self.focal_alpha) * out_prob**self.focal_gamma * (1 - out_prob + 1e-6).log()
-        pos_cost_class = -self.focal_alpha * (1 - out_prob)**self.focal_gamma * (out_prob + 1e-6).log()
-        return pos_cost_class[:, gt_labels] - neg_cost_class[:, gt_labels]
+        # focal-style cost of assigning each query to each target's class; the evaluation order
+        # ((scale * p^gamma) * log(. + 1e-6), positive minus negative term) fixes the float32 rounding
+        p = pred_logits.sigmoid()
+        gamma, alpha = self.focal_gamma, self.focal_alpha
+        negative = -(1 - alpha) * p**gamma * (1 - p + 1e-6).log()
+        positive = -alpha * (1 - p)**gamma * (p + 1e-6).log()
+        return positive[:, gt_labels] - negative[:, gt_labels]
 
     def calculate_bbox_cost(self, pred_boxes, gt_boxes, **kwargs):
-        return torch.cdist(pred_boxes, gt_boxes, p=1)
+        return torch.cdist(pred_boxes, gt_boxes, p=1)      # L1 distance between cxcywh boxes
 
     def calculate_giou_cost(self, pred_boxes, gt_boxes, **kwargs):
         return -_generalized_box_iou(_cxcywh_to_xyxy(pred_boxes), _cxcywh_to_xyxy(gt_boxes))
 
     @torch.no_grad()
     def calculate_cost(self, pred_boxes: Tensor, pred_logits: Tensor, gt_boxes: Tensor, gt_labels: Tensor):
-        cost_class = self.calculate_class_cost(pred_logits, gt_labels)
-        cost_bbox = self.calculate_bbox_cost(pred_boxes, gt_boxes)
-        cost_giou = self.calculate_giou_cost(pred_boxes, gt_boxes)
-        return self.cost_bbox * cost_bbox + self.cost_class * cost_class + self.cost_giou * cost_giou
+        terms = (self.cost_bbox * self.calculate_bbox_cost(pred_boxes, gt_boxes),
+                 self.cost_class * self.calculate_class_cost(pred_logits, gt_labels),
+                 self.cost_giou * self.calculate_giou_cost(pred_boxes, gt_boxes))
+        return terms[0] + terms[1] + terms[2]              # bbox + class, then + giou: upstream's order (:71)
 
     # -- assignment ----------------------------------------------------------------------------------------
     def _prepare(self, c: Tensor, gt_copy: int) -> Tuple[Tensor, int]:
