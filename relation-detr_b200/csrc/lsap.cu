@@ -143,7 +143,7 @@ lsap_kernel(const __grid_constant__ LsapLaunch launch)
             if (tid == 0) SR[i] = 1;
             const double u_i = u[i];
             const float *crow = c + (size_t)i * nc;
-            unsigned long long key = ~0ULL;          // loses against every real column (+inf included)
+            double best = INFINITY;                  // with code 0: loses against every real column (+inf included)
             unsigned code = 0;
             int col = -1;
             // kLsapBatch columns per thread at a time: all loads of a batch are issued before its first store, so
@@ -170,11 +170,11 @@ lsap_kernel(const __grid_constant__ LsapLaunch launch)
                     const double r = ((min_val + (double)cc[k]) - u_i) - vv[k];
                     double d = dd[k];
                     if (r < d) { path[j] = i; dist[j] = r; d = r; }
-                    const unsigned long long kk = order_key(d);
                     const unsigned cd = owner[k] < 0 ? (0x80000000u | (unsigned)t) : (0x7fffffffu - (unsigned)t);
-                    if (kk < key || (kk == key && cd > code)) { key = kk; code = cd; col = j; }
+                    if (d < best || (d == best && cd > code)) { best = d; code = cd; col = j; }
                 }
             }
+            unsigned long long key = col >= 0 ? order_key(best) : ~0ULL;   // integer image once per thread
             const unsigned my_code = code;
             const unsigned long long my_key = key;
             warp_pick(key, code);
