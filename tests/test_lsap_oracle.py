@@ -130,3 +130,22 @@ def test_eager_cost_terms_reproduce_the_reference_fixtures():
         z = np.load(path)
         c = m.calculate_cost(*[torch.as_tensor(z[k]) for k in ("pred_boxes", "pred_logits", "gt_boxes", "gt_labels")])
         assert np.array_equal(c.numpy(), z["cost"]), os.path.basename(path)
+
+
+def test_oracle_fuzz_with_hypothesis():
+    """Property: for any finite matrix (small integers, so that equal reduced costs are the rule, not the exception)
+    the oracle returns SciPy's pairs."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from hypothesis.extra.numpy import arrays
+
+    shapes = st.tuples(st.integers(1, 9), st.integers(1, 9))
+
+    @settings(max_examples=300, deadline=None)
+    @given(shapes.flatmap(lambda s: arrays(np.float64, s, elements=st.integers(-2, 2).map(float))))
+    def check(c):
+        rr, cc = linear_sum_assignment(c)
+        r, k = c_oracle.lsap(c)
+        assert np.array_equal(r, rr) and np.array_equal(k, cc)
+
+    check()
