@@ -92,6 +92,17 @@ int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes,
                         rdetr_stream_t stream);
 
 /*
+ * Process-wide tuning knobs of the MSDA kernels (not per-call state; safe to call from any thread).
+ * When Nq == S (encoder self-attention: every query is a pixel of the pyramid) and P == 4, L in {4, 5}, the
+ * library uses tiled kernels (one CTA per (image, head, 8x8 query tile), per-level windows in shared memory;
+ * DESIGN.md section 4).  mode 0 = automatic (default; also RDETR_MSDA_TILE in the environment), 1 = flat kernels
+ * only, 2 = tiled kernels whenever the shape allows.  rows = shared-memory rows (128 bytes each) a CTA may give
+ * to level windows; 0 restores the default.  Results do not depend on either knob beyond fp32 summation order.
+ */
+int rdetr_msda_set_tile_mode(int mode);
+int rdetr_msda_set_tile_rows(int rows);
+
+/*
  * Multi-scale deformable attention with the module prologue folded in ("N2"):
  * softmax over the L*P logits of every (b, q, head), sampling location = reference point + offset, and
  * the key-padding mask, which the reference computes with separate elementwise kernels before the op

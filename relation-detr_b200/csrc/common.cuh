@@ -110,6 +110,11 @@ struct Slice<float, 4> {
         const float4 t = ld_stream_f4(reinterpret_cast<const float4 *>(p));
         v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     }
+    __device__ __forceinline__ static void load_shared(const float *p, float (&v)[4])  // plain load (shared-memory window)
+    {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
     __device__ __forceinline__ static void store(float *p, const float (&v)[4])
     {
         *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -131,6 +136,10 @@ struct Slice<__nv_bfloat16, 8> {
     __device__ __forceinline__ static void load_stream(const __nv_bfloat16 *p, float (&v)[8])
     {
         unpack(ld_stream_u4(reinterpret_cast<const uint4 *>(p)), v);
+    }
+    __device__ __forceinline__ static void load_shared(const __nv_bfloat16 *p, float (&v)[8])
+    {
+        unpack(*reinterpret_cast<const uint4 *>(p), v);
     }
     __device__ __forceinline__ static void store(__nv_bfloat16 *p, const float (&v)[8])
     {

@@ -28,6 +28,13 @@ namespace rdetr {
 
 int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype);
 
+// msda_bwd_tile.cu: tiled backward for encoder self-attention (queries = pixels of the pyramid).  Returns -1 when
+// (L, P) is outside what it is built for.
+int msda_tile_mode();
+template <typename VT, typename IO>
+int launch_bwd_tile(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out, float *gv_f32,
+                    int B, int S, int M, int L, int Nq, int P, cudaStream_t stream);
+
 template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
@@ -237,6 +244,12 @@ template <typename VT, int CH, typename IO>
 static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
                       float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
+    // encoder self-attention (every query is a pixel of the pyramid): tiled kernel with shared-memory grad_value
+    // accumulators (msda_bwd_tile.cu); rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
+    if (Nq == S && msda_tile_mode() != 1) {
+        const int rc = launch_bwd_tile<VT, IO>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+        if (rc >= 0) return rc;
+    }
 #ifdef RDETR_TUNE_FWD
     const char *e = getenv("RDETR_MSDA_BWD_VARIANT");
     const int v = e ? atoi(e) : 0;

@@ -119,6 +119,13 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     SL::store(out + gp * D + lane * kCh, acc);
 }
 
+// msda_fwd_tile.cu: tiled forward for encoder self-attention (queries = pixels of the pyramid).  Returns -1 when
+// (L, P) is outside what it is built for.
+int msda_tile_mode();
+template <typename VT, int CH, typename IO>
+int launch_fwd_tile(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S, int M, int L,
+                    int Nq, int P, cudaStream_t stream);
+
 template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
 static int launch_fwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B,
                               int S, int M, int L, int Nq, int P, cudaStream_t stream)
@@ -145,6 +152,12 @@ template <typename VT, int CH, typename IO>
 static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S,
                       int M, int L, int Nq, int P, cudaStream_t stream)
 {
+    // encoder self-attention: tiled kernel with shared-memory value windows (msda_fwd_tile.cu);
+    // rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
+    if (Nq == S && msda_tile_mode() != 1) {
+        const int rc = launch_fwd_tile<VT, CH, IO>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (rc >= 0) return rc;
+    }
 #ifdef RDETR_TUNE_FWD
     // tuning builds only (tools/tune_fwd.py): CTA size from the environment
     const char *e = getenv("RDETR_MSDA_FWD_VARIANT");
