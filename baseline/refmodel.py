@@ -1,0 +1,109 @@
+"""Builds the reference's own models from its own classes (``baseline/_ref`` or ``/root/reference``).
+
+``build_relation_detr_r50`` restates the constructor calls of
+``configs/relation_detr/relation_detr_resnet50_800_1333.py`` (upstream) with ``weights=False`` for the backbone:
+executing the config file itself downloads ImageNet weights (``models/backbones/resnet.py:428-432``), and there is
+no network here.  Everything else -- classes, arguments, loss weights -- is the config's.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def reference_root() -> str | None:
+    for cand in (os.path.join(HERE, "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "models", "bricks")):
+            return cand
+    return None
+
+
+def available() -> bool:
+    return reference_root() is not None
+
+
+def activate() -> str:
+    """Puts the reference tree on sys.path (after registering the stand-ins for its missing imports)."""
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree not found: run `python baseline/install_reference.py` in the build container")
+    from . import stubs
+
+    stubs.install()
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return root
+
+
+def build_relation_detr_r50(num_classes: int = 91, num_queries: int = 900, hybrid_num_proposals: int = 1500,
+                            enc_layers: int = 6, dec_layers: int = 6, num_feature_levels: int = 4, denoising_nums: int = 100,
+                            min_size: int = 800, max_size: int = 1333):
+    """RelationDETR R50 as configs/relation_detr/relation_detr_resnet50_800_1333.py builds it, random init.
+    Call ``relation_detr_b200.install.install()`` BEFORE this to get the B200 operators inside."""
+    activate()
+    from torch import nn
+
+    from models.backbones.resnet import ResNetBackbone
+    from models.bricks.misc import FrozenBatchNorm2d
+    from models.bricks.position_encoding import PositionEmbeddingSine
+    from models.bricks.post_process import PostProcess
+    from models.bricks import relation_transformer as rt
+    from models.bricks.set_criterion import HybridSetCriterion
+    from models.detectors.relation_detr import RelationDETR
+    from models.matcher import hungarian_matcher as hm
+    from models.necks.channel_mapper import ChannelMapper
+
+    embed_dim, num_heads, dim_feedforward, hybrid_assign = 256, 8, 2048, 6
+    position_embedding = PositionEmbeddingSine(embed_dim // 2, temperature=10000, normalize=True, offset=-0.5)
+    backbone = ResNetBackbone("resnet50", weights=False, norm_layer=FrozenBatchNorm2d, return_indices=(1, 2, 3), freeze_indices=(0,))
+    neck = ChannelMapper(in_channels=backbone.num_channels, out_channels=embed_dim, num_outs=num_feature_levels)
+    transformer = rt.RelationTransformer(
+        encoder=rt.RelationTransformerEncoder(
+            encoder_layer=rt.RelationTransformerEncoderLayer(
+                embed_dim=embed_dim, n_heads=num_heads, dropout=0.0, activation=nn.ReLU(inplace=True),
+                n_levels=num_feature_levels, n_points=4, d_ffn=dim_feedforward),
+            num_layers=enc_layers),
+        decoder=rt.RelationTransformerDecoder(
+            decoder_layer=rt.RelationTransformerDecoderLayer(
+                embed_dim=embed_dim, n_heads=num_heads, dropout=0.0, activation=nn.ReLU(inplace=True),
+                n_levels=num_feature_levels, n_points=4, d_ffn=dim_feedforward),
+            num_layers=dec_layers, num_classes=num_classes),
+        num_classes=num_classes, num_feature_levels=num_feature_levels, two_stage_num_proposals=num_queries,
+        hybrid_num_proposals=hybrid_num_proposals)
+    matcher = hm.HungarianMatcher(cost_class=2, cost_bbox=5, cost_giou=2, focal_alpha=0.25, focal_gamma=2.0)
+    weight_dict = {"loss_class": 1, "loss_bbox": 5, "loss_giou": 2}
+    weight_dict.update({"loss_class_dn": 1, "loss_bbox_dn": 5, "loss_giou_dn": 2})
+    aux = {}
+    for i in range(transformer.decoder.num_layers - 1):
+        aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+    weight_dict.update(aux)
+    weight_dict.update({"loss_class_enc": 1, "loss_bbox_enc": 5, "loss_giou_enc": 2})
+    weight_dict.update({k + "_hybrid": v for k, v in weight_dict.items()})
+    criterion = HybridSetCriterion(num_classes=num_classes, matcher=matcher, weight_dict=weight_dict, alpha=0.25, gamma=2.0)
+    postprocessor = PostProcess(select_box_nums_for_evaluation=300)
+    model = RelationDETR(backbone=backbone, neck=neck, position_embedding=position_embedding, transformer=transformer,
+                         criterion=criterion, postprocessor=postprocessor, num_classes=num_classes, num_queries=num_queries,
+                         hybrid_assign=hybrid_assign, denoising_nums=denoising_nums, min_size=min_size, max_size=max_size)
+    return model, weight_dict
+
+
+def synthetic_batch(batch: int, device, seed: int = 0, height: int = 800, width: int = 1333, boxes_per_image: int = 10,
+                    num_classes: int = 91):
+    """Fixed-size synthetic images and targets: ``randn(3,H,W)`` images, ``boxes_per_image``
+    random valid xyxy boxes in pixels and labels in [0, num_classes)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    images, targets = [], []
+    for _ in range(batch):
+        images.append(torch.randn((3, height, width), generator=g).to(device))
+        cx = torch.rand((boxes_per_image,), generator=g) * (width * 0.8) + width * 0.1
+        cy = torch.rand((boxes_per_image,), generator=g) * (height * 0.8) + height * 0.1
+        w = torch.rand((boxes_per_image,), generator=g) * (width * 0.15) + 8
+        h = torch.rand((boxes_per_image,), generator=g) * (height * 0.15) + 8
+        boxes = torch.stack([(cx - w / 2).clamp(min=0), (cy - h / 2).clamp(min=0), (cx + w / 2).clamp(max=width), (cy + h / 2).clamp(max=height)], -1)
+        labels = torch.randint(0, num_classes, (boxes_per_image,), generator=g)
+        targets.append({"boxes": boxes.to(device), "labels": labels.to(device)})
+    return images, targets

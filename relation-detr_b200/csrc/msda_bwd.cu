@@ -246,7 +246,7 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
 {
     // encoder self-attention (every query is a pixel of the pyramid): tiled kernel with shared-memory grad_value
     // accumulators (msda_bwd_tile.cu); rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
-    if (Nq == S && msda_tile_mode() != 1) {
+    if (Nq == S && msda_tile_mode() == 2) {
         const int rc = launch_bwd_tile<VT, IO>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
         if (rc >= 0) return rc;
     }

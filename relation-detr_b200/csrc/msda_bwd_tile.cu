@@ -9,19 +9,26 @@
 //     item it measures the window of every level that the tile's samples touch and gives the windows that fit
 //     shared-memory rows (coarsest level first);
 //   * grad_value of a resident level is accumulated in those rows with PLAIN ld.shared / fma / st.shared -- no
-//     shared-memory atomics (a CAS loop on this part: 15 clk per row, slower than L2) -- by giving every
-//     resident level to exactly one warp of four "scatter warps" whose 32 lanes are the 32 channels of the head:
-//     a lane only ever touches its own channel, a warp handles one sample at a time, the four corners of a
-//     sample are four different pixels, and no other warp touches that level.  Program order within a thread is
-//     the only ordering needed;
+//     shared-memory atomics (fp32 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop on sm_100a: 15 clk per
+//     row, slower than L2) -- by one "scatter warp" whose four 8-lane quarters (8 lanes x 4 channels = one
+//     128-byte row) each own a different level: a quarter handles one sample at a time, the four corners of a
+//     sample are four different pixels, and nobody else touches that level's window.  Program order within a
+//     thread is the only ordering needed;
 //   * the window is flushed once per item: one red.global.add.v4.f32 per touched (pixel, head) row instead of
-//     one per corner -- 5-15x fewer L2 reductions for encoder-like inputs;
+//     one per corner -- measured 5.9x fewer L2 reductions at configs[1] (profiles/r02b_ncu_summary_tile_v1.md);
 //   * the other eight "gather warps" do what the flat kernel does (8 lanes x 4 channels per (query, head),
 //     value corners gathered with 16-byte read-only loads, grad_loc / grad_attn by xor-shuffles) at the same
 //     time, and issue direct reductions only for levels that are not resident.  Their per-sample results stay
 //     in registers (lane j of a group keeps samples j*K .. j*K+K-1) and leave as dense 16-byte stores.
 //
 // Correct for any input: a level without locality (window too large) simply takes the direct path.
+//
+// STATUS (round 2, measured on B200, profiles/r02a..r02c): parity-green but SLOWER than the flat kernel --
+// 3.3 ms vs 1.8 ms at configs[1].  The flat kernel is bound by the L2 reduction rate (50 G rows/s) at 67 % issue
+// utilisation; this kernel removes 83 % of the reductions but needs 1 300-1 700 warp instructions per (query, head)
+// against 966 (records, windows, a second pass over every sample by the scatter warp, barriers between the
+// phases: 30 % of the stall samples) and becomes issue / latency bound at 2-3 CTAs per SM.  It is therefore only
+// used when rdetr_msda_set_tile_mode(2) / RDETR_MSDA_TILE=2 asks for it.  DESIGN.md section 7 has the numbers.
 #include <atomic>
 #include <cstdlib>
 
@@ -30,7 +37,7 @@
 namespace rdetr {
 
 constexpr int kBwdTileGatherWarps = 8;
-constexpr int kBwdTileScatterWarps = 4;
+constexpr int kBwdTileScatterWarps = 1;
 constexpr int kBwdTileThreads = 32 * (kBwdTileGatherWarps + kBwdTileScatterWarps);
 
 template <typename VT, int L, int P, typename IO, int MINB>
@@ -72,15 +79,15 @@ msda_bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ s
 
         // ---- phase 1: records, queries, windows; grad_out rows of the tile ---------------------------
         tile_phase1<L, P, G, kBwdTileThreads>(io, geo, b, m, tile, S, M, Nq, s_rec, s_q, s_bb);
+        __syncthreads();
+        if (tid == kBwdTileThreads - 1) tile_place_levels<L>(s_bb, s_place, cap_rows);
         for (int i = tid; i < kTileQ * kLanes; i += kBwdTileThreads) {
             const int slot = i / kLanes, l8 = i % kLanes;
-            const int q = tile_query(geo, L, Nq, tile, slot);
+            const int q = s_q[slot];
             float g4[CH] = {0.f, 0.f, 0.f, 0.f};
             if (q >= 0) SL::load_stream(grad_out + (((long long)b * Nq + q) * M + m) * D + l8 * CH, g4);
             *reinterpret_cast<float4 *>(s_g + slot * D + l8 * CH) = make_float4(g4[0], g4[1], g4[2], g4[3]);
         }
-        __syncthreads();
-        if (tid == 0) tile_place_levels<L>(s_bb, s_place, cap_rows);
         __syncthreads();
 
         if (warp < kBwdTileGatherWarps) {
@@ -205,17 +212,24 @@ msda_bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ s
                 }
             }
         } else {
-            // ---- scatter warps: exclusive shared-memory accumulation of resident levels ------------------
-            const int c = lane;  // channel
-            for (int l = warp - kBwdTileGatherWarps; l < L; l += kBwdTileScatterWarps) {
+            // ---- scatter warp: exclusive shared-memory accumulation of the resident levels ------------------
+            // quarter k of the warp (8 lanes x 4 channels = one 128-byte row per access) owns level 4*sweep + k:
+            // the four quarters never share a window, a quarter handles one sample at a time, and the four
+            // corners of a sample are four different pixels -> plain ld.shared / fma / st.shared is race-free.
+            const int qk = lane >> 3, l8 = lane & 7;
+#pragma unroll 1
+            for (int sweep = 0; sweep * 4 < L; ++sweep) {
+                const int lv = sweep * 4 + qk;
+                const bool mine = lv < L && s_place[lv < L ? lv : 0].resident;
+                if (!__any_sync(0xffffffffu, mine)) continue;
+                const int l = mine ? lv : 0;  // lanes without a level walk level 0's records with every corner masked off
                 const TilePlace pl = s_place[l];
-                if (!pl.resident) continue;
-                float *accl = s_acc + (long long)pl.off * D + c;
+                float *accl = s_acc + (long long)pl.off * D + l8 * CH;
                 const int rowpitch = pl.bw * D;
-                // records and the grad_out element of slot+1 are fetched before slot is accumulated: the compiler
+                // records and the grad_out slice of slot+1 are fetched before slot is accumulated: the compiler
                 // cannot move shared-memory loads above the accumulator stores on its own (they may alias)
                 float4 rn[P];
-                float gn = s_g[c];
+                float4 gn = *reinterpret_cast<const float4 *>(s_g + l8 * CH);
                 int qn = s_q[0];
 #pragma unroll
                 for (int p = 0; p < P; ++p) rn[p] = s_rec[l * P + p];
@@ -224,10 +238,10 @@ msda_bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ s
                     float4 r[P];
 #pragma unroll
                     for (int p = 0; p < P; ++p) r[p] = rn[p];
-                    const float gq = gn;
+                    const float4 gq = gn;
                     const int q = qn;
                     if (slot + 1 < kTileQ) {
-                        gn = s_g[(slot + 1) * D + c];
+                        gn = *reinterpret_cast<const float4 *>(s_g + (slot + 1) * D + l8 * CH);
                         qn = s_q[slot + 1];
 #pragma unroll
                         for (int p = 0; p < P; ++p) rn[p] = s_rec[(slot + 1) * kRecStride + l * P + p];
@@ -236,21 +250,23 @@ msda_bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ s
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
                         const RecView rv = unpack_rec(r[p].x);
-                        if (rv.vm == 0) continue;
-                        const float lw = r[p].y, lh = r[p].z;
+                        const unsigned vm = mine ? rv.vm : 0u;
+                        if (!__any_sync(0xffffffffu, vm != 0u)) continue;
+                        const float lw = r[p].y, lh = r[p].z, a = r[p].w;
                         const float hw = 1.f - lw, hh = 1.f - lh;
-                        const float tg = gq * r[p].w;
-                        float *p0 = accl + ((rv.h0 - pl.y0) * pl.bw + (rv.w0 - pl.x0)) * D;
-                        float *p1 = p0 + D, *p2 = p0 + rowpitch, *p3 = p2 + D;
+                        const float w0 = (hh * hw) * a, w1 = (hh * lw) * a, w2 = (lh * hw) * a, w3 = (lh * lw) * a;
+                        float4 *p0 = reinterpret_cast<float4 *>(accl + ((rv.h0 - pl.y0) * pl.bw + (rv.w0 - pl.x0)) * D);
+                        float4 *p1 = p0 + D / 4, *p2 = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p0) + rowpitch), *p3 = p2 + D / 4;
                         // the four corners are four different pixels: load all, then store all
-                        const float a0 = (rv.vm & 1u) ? *p0 : 0.f;
-                        const float a1 = (rv.vm & 2u) ? *p1 : 0.f;
-                        const float a2 = (rv.vm & 4u) ? *p2 : 0.f;
-                        const float a3 = (rv.vm & 8u) ? *p3 : 0.f;
-                        if (rv.vm & 1u) *p0 = fmaf(hh * hw, tg, a0);
-                        if (rv.vm & 2u) *p1 = fmaf(hh * lw, tg, a1);
-                        if (rv.vm & 4u) *p2 = fmaf(lh * hw, tg, a2);
-                        if (rv.vm & 8u) *p3 = fmaf(lh * lw, tg, a3);
+                        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+                        if (vm & 1u) a0 = *p0;
+                        if (vm & 2u) a1 = *p1;
+                        if (vm & 4u) a2 = *p2;
+                        if (vm & 8u) a3 = *p3;
+                        if (vm & 1u) *p0 = make_float4(fmaf(w0, gq.x, a0.x), fmaf(w0, gq.y, a0.y), fmaf(w0, gq.z, a0.z), fmaf(w0, gq.w, a0.w));
+                        if (vm & 2u) *p1 = make_float4(fmaf(w1, gq.x, a1.x), fmaf(w1, gq.y, a1.y), fmaf(w1, gq.z, a1.z), fmaf(w1, gq.w, a1.w));
+                        if (vm & 4u) *p2 = make_float4(fmaf(w2, gq.x, a2.x), fmaf(w2, gq.y, a2.y), fmaf(w2, gq.z, a2.z), fmaf(w2, gq.w, a2.w));
+                        if (vm & 8u) *p3 = make_float4(fmaf(w3, gq.x, a3.x), fmaf(w3, gq.y, a3.y), fmaf(w3, gq.z, a3.z), fmaf(w3, gq.w, a3.w));
                     }
                 }
             }
@@ -259,21 +275,22 @@ msda_bwd_tile_kernel(const VT *__restrict__ value, const int64_t *__restrict__ s
 
         // ---- flush: one vector reduction per touched (pixel, head) row; rows are left zeroed ---------------
         {
-            const int l8 = tid & 7;
+            const int l8 = lane & 7;
             float *gvb = grad_value_f32 + ((long long)b * S * M + m) * D + l8 * CH;
+#pragma unroll 1
             for (int l = 0; l < L; ++l) {
                 const TilePlace pl = s_place[l];
                 if (!pl.resident) continue;
-                const int rows = pl.bw * pl.bh;
                 const int Wl = geo.W[l], st = geo.start[l];
-                for (int r = tid >> 3; r < rows; r += kBwdTileThreads / 8) {
-                    float4 *cell = reinterpret_cast<float4 *>(s_acc + (long long)(pl.off + r) * D + l8 * CH);
-                    const float4 v = *cell;
-                    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
-                        const int ry = r / pl.bw, rx = r - ry * pl.bw;
-                        const long long pix = st + (long long)(pl.y0 + ry) * Wl + (pl.x0 + rx);
-                        red_add_f32x4(gvb + pix * pix_stride, v.x, v.y, v.z, v.w);
-                        *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int ry = warp; ry < pl.bh; ry += kBwdTileThreads / 32) {
+                    const long long pixrow = st + (long long)(pl.y0 + ry) * Wl + pl.x0;
+                    for (int rx = lane >> 3; rx < pl.bw; rx += 4) {
+                        float4 *cell = reinterpret_cast<float4 *>(s_acc + (long long)(pl.off + ry * pl.bw + rx) * D + l8 * CH);
+                        const float4 v = *cell;
+                        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) {
+                            red_add_f32x4(gvb + (pixrow + rx) * pix_stride, v.x, v.y, v.z, v.w);
+                            *cell = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
             }
@@ -305,10 +322,10 @@ template <typename VT, int L, int P, typename IO>
 static int launch_bwd_tile_lp(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
                               float *gv_f32, int B, int S, int M, int Nq, cudaStream_t stream)
 {
-    constexpr int MINB = 2;
+    constexpr int MINB = 3;
     auto kern = msda_bwd_tile_kernel<VT, L, P, IO, MINB>;
     int cap_rows = g_tile_cap_rows.load(std::memory_order_relaxed);
-    if (cap_rows <= 0) cap_rows = 640;
+    if (cap_rows <= 0) cap_rows = 384;
     const size_t smem = (size_t)kTileQ * (L * P + 1) * sizeof(float4) + (size_t)kTileQ * 32 * sizeof(float) + (size_t)cap_rows * 128;
     if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(msda_bwd_tile)"))

@@ -154,7 +154,7 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
 {
     // encoder self-attention: tiled kernel with shared-memory value windows (msda_fwd_tile.cu);
     // rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
-    if (Nq == S && msda_tile_mode() != 1) {
+    if (Nq == S && msda_tile_mode() == 2) {
         const int rc = launch_fwd_tile<VT, CH, IO>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
         if (rc >= 0) return rc;
     }

@@ -7,6 +7,12 @@
 // value rows a tile needs form a small window per level; the CTA copies the windows that fit its budget into
 // shared memory once (each row is then read ~5-17 times) and gathers from there; levels whose window does not fit
 // (no locality) are gathered from global memory exactly as the flat kernel does.
+//
+// STATUS (round 2, measured on B200, profiles/r02a..r02b): parity-green but SLOWER than the flat kernel -- 1.44 ms vs
+// 0.58-0.61 ms at configs[1].  The flat kernel already issues at 76 % of the schedulers' rate; this one needs 518 warp
+// instructions per (query, head) against 344 (records, windows, staging, four barriers per item) at 25 % occupancy and
+// its time scales with 1 / (CTAs per SM): latency bound.  Staging through the LSU also costs the L1 wavefronts it was
+// meant to save (a TMA box copy would not).  Only used when rdetr_msda_set_tile_mode(2) / RDETR_MSDA_TILE=2 asks for it.
 #include "msda_tile.cuh"
 
 namespace rdetr {

@@ -107,7 +107,7 @@ __device__ __forceinline__ TapHW make_tap_hw(float lx, float ly, int H, int W)
 
 __device__ __forceinline__ float4 pack_rec(const TapHW &t, float a)
 {
-    if (t.vm == 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t.vm == 0) return make_float4(0.f, 0.f, 0.f, a);  // the weight survives: the fused softmax backward needs it
     const unsigned bits = (unsigned)(t.h0 + 1) | ((unsigned)(t.w0 + 1) << 14) | (t.vm << 28);
     return make_float4(__uint_as_float(bits), t.lw, t.lh, a);
 }
@@ -152,7 +152,9 @@ __device__ __forceinline__ void tile_phase1(const IO &io, const TileGeom &geo, i
     const float inv_P = 1.0f / (float)P;
     for (int base = 0; base < kTileQ; base += kGroups) {  // same trip count for every thread: shuffles below are warp-wide
         const int slot = base + grp;
-        const int q = slot < kTileQ ? tile_query(geo, L, Nq, tile, slot) : -1;
+        int q = -1;
+        if (j == 0 && slot < kTileQ) q = tile_query(geo, L, Nq, tile, slot);
+        q = __shfl_sync(0xffffffffu, q, lane & ~(G - 1));  // one evaluation per query slot
         const bool live = q >= 0 && j < LP;
         const int l = j < LP ? j / P : L - 1;
         const long long bq = (long long)b * Nq + (q >= 0 ? q : 0);

@@ -51,7 +51,7 @@ def test_tiled_fp32_matches_oracle_and_flat(levels, loc_kind, rows):
         assert relmax(r["grad_loc"], ref["grad_loc"]) <= 1e-4
     # the tiled and the flat kernels run the same per-sample arithmetic: only summation order differs
     assert maxabs(r["out"], flat["out"]) <= 2e-6
-    assert relmax(r["grad_value"], flat["grad_value"]) <= 2e-6
+    assert relmax(r["grad_value"], flat["grad_value"]) <= 1e-5
     assert relmax(r["grad_attn"], flat["grad_attn"]) <= 1e-6
     assert relmax(r["grad_loc"], flat["grad_loc"]) <= 1e-6
 

@@ -241,6 +241,47 @@ __global__ void sincosf_chain(int iters, float* sink)
     if (s == 123.456f) sink[0] = s;
 }
 
+
+// Mixed scatter: of every 4 consecutive 8-lane groups, TMAQ use the TMA reduce path (stage the row in shared memory,
+// cp.reduce.async.bulk.add.f32 of 128 bytes) and the rest the LSU path (red.global.add.v4.f32).  If the two paths had
+// independent ceilings the combined row rate would exceed either alone.
+template <int TMAQ, int DEPTH>
+__global__ void mixed_red_rows(float* table, uint32_t nrows, int iters)
+{
+    extern __shared__ __align__(128) float stage[];  // [warps][DEPTH][4 groups][32 floats]
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp_in_cta = threadIdx.x >> 5;
+    const uint32_t group = tid / 8, g = lane >> 3, l8 = lane & 7;
+    const bool use_tma = (int)g < TMAQ;
+    float* mystage = stage + (size_t)warp_in_cta * DEPTH * 4 * 32;
+    uint32_t seed = group * 2654435761u + 777u;
+    int slot = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+            seed = hash32(seed + u);
+            const uint32_t row = seed % nrows;
+            if (use_tma) {
+                if (l8 == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(DEPTH - 1) : "memory");
+                __syncwarp(TMAQ == 4 ? 0xffffffffu : ((1u << (8 * TMAQ)) - 1u));
+                float* dst = mystage + (slot * 4 + g) * 32;
+                *reinterpret_cast<float4*>(dst + l8 * 4) = make_float4(1.f, 1.f, 1.f, 1.f);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp(TMAQ == 4 ? 0xffffffffu : ((1u << (8 * TMAQ)) - 1u));
+                if (l8 == 0) {
+                    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(table + (size_t)row * 32), "r"(saddr) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                slot = (slot + 1) % DEPTH;
+            } else {
+                red4(table + (size_t)row * 32 + l8 * 4, 1.0f);
+            }
+        }
+    }
+    if (use_tma && l8 == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <typename F>
 static float time_ms(F f, int reps = 5)
 {
@@ -326,6 +367,20 @@ int main()
         float ms = time_ms([&] { tma_red_rows<DEPTH><<<blocks, threads, smem>>>(ftab, c.rows, it2); });
         double rows = nthreads / 8 * it2 * 8;
         printf("TMA cp.reduce.async.bulk 128B rows, %-22s : %8.3f ms  %7.2f Grows/s  %7.2f TB/s\n", c.name, ms, rows / ms / 1e6, rows * 128 / ms / 1e9);
+    }
+    {   // LSU red.v4 and TMA bulk reduce at the same time: independent ceilings?
+        const int it2 = 16;
+        constexpr int DEPTH = 4;
+        const size_t smem = (size_t)(threads / 32) * DEPTH * 4 * 32 * sizeof(float);
+        struct { const char* name; uint32_t rows; } mc[] = {{"17k rows (level-2-like, 64 tables)", 1050u * 64}, {"183MB (no contention)", (uint32_t)big_rows}};
+        for (auto& c : mc) {
+            float ms; double rows = nthreads / 8 * it2 * 8;
+#define MIXED(Q) CK(cudaFuncSetAttribute(mixed_red_rows<Q, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            ms = time_ms([&] { mixed_red_rows<Q, DEPTH><<<blocks, threads, smem>>>(ftab, c.rows, it2); }); \
+            printf("mixed scatter, %d of 4 groups via TMA reduce, %-36s : %8.3f ms  %7.2f Grows/s\n", Q, c.name, ms, rows / ms / 1e6);
+            MIXED(0) MIXED(1) MIXED(2) MIXED(3) MIXED(4)
+#undef MIXED
+        }
     }
     {
         const int nrows = 1024;  // 128 KB table per CTA
