@@ -25,7 +25,16 @@ def available() -> bool:
 
 
 def activate() -> str:
-    """Puts the reference tree on sys.path (after registering the stand-ins for its missing imports)."""
+    """Puts the reference tree on sys.path (after registering the stand-ins for its missing imports) and imports
+    ``models.bricks.ms_deform_attn`` once with its import-time JIT build short-circuited.
+
+    Upstream builds its CUDA extension at import time whenever a GPU is visible (``ms_deform_attn.py:14-26``); against
+    this image's torch 2.11 that build runs nvcc for minutes and then fails, after which upstream
+    silently uses ``multi_scale_deformable_attn_pytorch``.  We make the doomed build fail immediately instead --
+    ``torch.utils.cpp_extension.load`` raises for the duration of that one import -- which leaves the reference in
+    exactly the state it reaches on its own (``_C is None``).  No reference file is edited.
+    ``set_reference_extension("prebuilt")`` can then hand it its own kernel, compiled from its unmodified sources by
+    ``oracle/build_ref_cuda.py``."""
     root = reference_root()
     if root is None:
         raise RuntimeError("reference tree not found: run `python baseline/install_reference.py` in the build container")
@@ -34,7 +43,46 @@ def activate() -> str:
     stubs.install()
     if root not in sys.path:
         sys.path.insert(0, root)
+    if "models.bricks.ms_deform_attn" not in sys.modules:
+        import warnings
+
+        import torch.utils.cpp_extension as cpp_ext
+
+        real_load = cpp_ext.load
+
+        def _no_jit(*a, **k):
+            raise RuntimeError("JIT build skipped by baseline/refmodel.py: upstream's extension does not compile against torch 2.11 "
+                               "(SURVEY.md F1); the reference falls back to multi_scale_deformable_attn_pytorch as it does on its own")
+
+        cpp_ext.load = _no_jit
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                import models.bricks.ms_deform_attn  # noqa: F401
+        finally:
+            cpp_ext.load = real_load
     return root
+
+
+def set_reference_extension(mode: str = "none") -> str:
+    """Which MSDA path the UNMODIFIED reference modules take on the GPU: ``"none"`` = its grid_sample path (what
+    upstream effectively runs on this image), ``"prebuilt"`` = its own CUDA kernel from ``oracle/_ref`` (unmodified
+    sources recompiled for sm_100a).  Sets the module global the reference itself consults (``ms_deform_attn.py:358``);
+    returns the mode actually in effect."""
+    activate()
+    import models.bricks.ms_deform_attn as ref_msda
+
+    if mode == "prebuilt":
+        root = os.path.dirname(HERE)
+        if root not in sys.path:
+            sys.path.insert(0, root)
+        from oracle import build_ref_cuda
+
+        ext = build_ref_cuda.load_prebuilt()
+        ref_msda._C = ext
+        return "prebuilt" if ext is not None else "none"
+    ref_msda._C = None
+    return "none"
 
 
 def build_relation_detr_r50(num_classes: int = 91, num_queries: int = 900, hybrid_num_proposals: int = 1500,

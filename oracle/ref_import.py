@@ -2,15 +2,13 @@
 
 TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box, so nothing that runs
 there may call this; it is used by ``make_golden.py`` and by CPU tests that skip when the reference
-tree is absent.  ``util.misc`` is replaced by a 4-line stand-in because the real module drags in
-packages that are not installed here; the stand-in keeps the semantics of
-``util/misc.py:31-35``.
+tree is absent.  The third-party packages the reference imports but this image lacks are replaced by the inert
+stand-ins of ``baseline/stubs.py``; the reference's own modules are imported unmodified.
 """
 from __future__ import annotations
 
 import os
 import sys
-import types
 import warnings
 
 REFERENCE_ROOT = os.environ.get("RDETR_REFERENCE_ROOT", "/root/reference")
@@ -28,18 +26,15 @@ def load():
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    if "util.misc" not in sys.modules:
-        util_pkg = sys.modules.get("util") or types.ModuleType("util")
-        util_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "util")]
-        misc = types.ModuleType("util.misc")
+    # the reference's util.misc drags in packages that are not installed here: register the
+    # inert stand-ins of baseline/stubs.py for them and import the REAL util.misc (one mechanism for every
+    # consumer of the reference tree in this repository: golden generation, CPU tests, the reference arm)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from baseline import stubs
 
-        def inverse_sigmoid(x, eps: float = 1e-3):
-            x = x.clamp(min=0, max=1)
-            return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
-
-        misc.inverse_sigmoid = inverse_sigmoid
-        sys.modules["util"] = util_pkg
-        sys.modules["util.misc"] = misc
+    stubs.install()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         from models.bricks.ms_deform_attn import (MultiScaleDeformableAttention,

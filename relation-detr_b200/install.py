@@ -5,6 +5,10 @@
 ``models/detectors/relation_detr`` and the DINO++ / Deformable-DETR++ configs build with the new
 path without editing them.  Call it before the config file is executed (configs instantiate the
 model at import time, ``util/lazy_load.py``).  See INTEGRATION.md.
+
+It fails loudly: a module of the reference that cannot be imported raises (the reference itself falls back
+silently when its extension does not build, ``ms_deform_attn.py:23-26`` -- exactly the failure mode this
+package refuses to have).  ``strict=False`` restores the lenient behaviour and returns what it skipped.
 """
 from __future__ import annotations
 
@@ -27,34 +31,70 @@ _MSDA_USERS = (
 # modules of the reference that bind HungarianMatcher by name (the configs import it from the first one)
 _MATCHER_USERS = ("models.matcher.hungarian_matcher",)
 
+_saved = {}  # "module.attr" -> the reference's own object, for uninstall()
 
-def install(reference_root: str | None = None, strict: bool = False, matcher_too: bool = True) -> list:
-    """Returns the list of ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
+
+class InstallReport(list):
+    """The rebound ``module.attribute`` names (a list, as before) plus ``skipped``: modules that failed to import
+    (only ever non-empty with ``strict=False``)."""
+
+    def __init__(self, rebound=(), skipped=()):
+        super().__init__(rebound)
+        self.skipped = list(skipped)
+
+
+def install(reference_root: str | None = None, strict: bool = True, matcher_too: bool = True) -> InstallReport:
+    """Returns the ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
     ``HungarianMatcher`` (device-resident matching): its index tensors are CUDA
     tensors, which every use in ``models/bricks/set_criterion.py`` accepts."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
-    rebound = []
+    report = InstallReport()
+
+    def rebind(mod, name, attr, repl):
+        key = f"{name}.{attr}"
+        if key not in _saved:
+            _saved[key] = getattr(mod, attr)
+        setattr(mod, attr, repl)
+        report.append(key)
+
     for name in _MSDA_USERS:
         try:
             mod = importlib.import_module(name)
-        except Exception:
+        except Exception as e:
             if strict:
-                raise
+                raise RuntimeError(f"relation_detr_b200.install: cannot import the reference module {name!r} "
+                                   f"({type(e).__name__}: {e}); nothing of it was rebound") from e
+            report.skipped.append(f"{name} ({type(e).__name__}: {e})")
             continue
         for attr, repl in (("MultiScaleDeformableAttention", modules.MultiScaleDeformableAttention),
                            ("MultiScaleDeformableAttnFunction", ops.MultiScaleDeformableAttnFunction),
                            ("PositionRelationEmbedding", modules.PositionRelationEmbedding)):
             if hasattr(mod, attr):
-                setattr(mod, attr, repl)
-                rebound.append(f"{name}.{attr}")
+                rebind(mod, name, attr, repl)
     for name in _MATCHER_USERS if matcher_too else ():
         try:
             mod = importlib.import_module(name)
-        except Exception:
+        except Exception as e:
             if strict:
-                raise
+                raise RuntimeError(f"relation_detr_b200.install: cannot import the reference module {name!r} "
+                                   f"({type(e).__name__}: {e})") from e
+            report.skipped.append(f"{name} ({type(e).__name__}: {e})")
             continue
-        mod.HungarianMatcher = matcher.HungarianMatcher
-        rebound.append(f"{name}.HungarianMatcher")
-    return rebound
+        rebind(mod, name, "HungarianMatcher", matcher.HungarianMatcher)
+    if strict and not report:
+        raise RuntimeError("relation_detr_b200.install: no name of the reference was rebound")
+    return report
+
+
+def uninstall() -> list:
+    """Puts the reference's own classes back (models built in between keep whatever they were built with)."""
+    restored = []
+    for key, obj in list(_saved.items()):
+        name, attr = key.rsplit(".", 1)
+        mod = sys.modules.get(name)
+        if mod is not None:
+            setattr(mod, attr, obj)
+            restored.append(key)
+        del _saved[key]
+    return restored

@@ -124,7 +124,10 @@ def test_tiled_fused_prologue_matches_oracle_and_flat(ref_dim, with_mask, levels
         got[mode] = (out.detach(), v.grad, off.grad, z.grad)
     out, gv, goff, gz = got[2]
     rel = lambda a, b: ((a.double() - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
-    assert (out.double() - want_out).abs().max().item() <= 1e-5
+    # 1 424 queries x 256 outputs: the bound is the reference's own fp32 noise at this size (2.2e-5
+    # for the 800x1333 pyramid), not the 1e-5 of the 45-query cases; the flat kernels are held to the same data below
+    assert (out.double() - want_out).abs().max().item() <= 3e-5
+    assert (got[1][0].double() - want_out).abs().max().item() <= 3e-5
     assert rel(gv, want_gv) <= 1e-4 and rel(gz, want_gz) <= 1e-4
     bad = ((goff.double() - want_go).abs() > 1e-4 * want_go.abs().max()).double().mean().item()
     assert bad <= 2e-3, bad

@@ -1,0 +1,174 @@
+"""Integration parity against the REAL reference classes.
+
+The unmodified upstream tree travels to the GPU box as ``baseline/_ref`` (``baseline/install_reference.py``).
+Each test builds a reference module twice -- once as upstream wrote it (its CUDA extension does not build against
+this torch, so it runs its own ``multi_scale_deformable_attn_pytorch`` / eager relation embedding on the GPU) and
+once after ``relation_detr_b200.install.install()`` -- loads the same weights into both (``strict=True``), and
+compares outputs and every parameter gradient on the same seeded inputs.
+"""
+import copy
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from baseline import refmodel  # noqa: E402
+from relation_detr_b200 import install as rinstall  # noqa: E402
+from relation_detr_b200 import modules, workloads  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refmodel.available(), reason="baseline/_ref not installed")]
+DEV = "cuda:0"
+LEVELS = ((25, 34), (13, 17), (7, 9), (4, 5))
+
+
+@pytest.fixture(autouse=True)
+def _fp32_matmuls():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    rinstall.uninstall()
+
+
+def _pair(build):
+    """(reference-built module, module built after install()) with identical weights."""
+    refmodel.activate()
+    rinstall.uninstall()
+    torch.manual_seed(0)
+    ref = build().to(DEV)
+    report = rinstall.install()
+    assert not report.skipped and "models.bricks.relation_transformer.PositionRelationEmbedding" in report
+    torch.manual_seed(0)
+    ours = build().to(DEV)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    rinstall.uninstall()
+    return ref, ours
+
+
+def _grads(mod):
+    return {n: p.grad.detach().clone() for n, p in mod.named_parameters() if p.grad is not None}
+
+
+def _assert_close(a, b, tol, what):
+    den = max(b.abs().max().item(), 1e-12)
+    err = (a.double() - b.double()).abs().max().item() / den
+    assert err <= tol, f"{what}: rel-to-max error {err:.3e} > {tol}"
+
+
+def test_encoder_layer_matches_the_unmodified_reference():
+    def build():
+        from models.bricks import relation_transformer as rt
+        return rt.RelationTransformerEncoderLayer(embed_dim=256, d_ffn=512, dropout=0.0, n_heads=8,
+                                                  activation=torch.nn.ReLU(inplace=True), n_levels=4, n_points=4)
+
+    ref, ours = _pair(build)
+    assert isinstance(ours.self_attn, modules.MultiScaleDeformableAttention)
+    assert not isinstance(ref.self_attn, modules.MultiScaleDeformableAttention)
+    with torch.no_grad():  # give the offsets / attention projections non-trivial weights (they start at zero)
+        for m in (ref, ours):
+            torch.manual_seed(1)
+            m.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+            m.self_attn.attention_weights.weight.normal_(0, 0.05)
+    ss, lsi = workloads.shape_tensors(LEVELS, DEV)
+    S = int(ss.prod(1).sum())
+    g = torch.Generator(device=DEV).manual_seed(3)
+    query = torch.randn((2, S, 256), device=DEV, generator=g)
+    pos = torch.randn((2, S, 256), device=DEV, generator=g) * 0.1
+    refp = workloads.full_reference_points(LEVELS, DEV)[None, :, None, :].expand(2, S, 4, 2).contiguous()
+    mask = torch.zeros((2, S), dtype=torch.bool, device=DEV)
+    mask[1, -40:] = True
+    go = torch.randn((2, S, 256), device=DEV, generator=g)
+    outs = []
+    for m in (ref, ours):
+        out = m(query=query, query_pos=pos, reference_points=refp, spatial_shapes=ss, level_start_index=lsi, query_key_padding_mask=mask)
+        out.backward(go)
+        outs.append(out.detach())
+    _assert_close(outs[1], outs[0], 2e-5, "encoder layer output")
+    gr, go_ = _grads(ref), _grads(ours)
+    assert gr.keys() == go_.keys()
+    for n in gr:
+        _assert_close(go_[n], gr[n], 2e-4, f"grad {n}")
+
+
+def test_decoder_matches_the_unmodified_reference():
+    def build():
+        from models.bricks import relation_transformer as rt
+        layer = rt.RelationTransformerDecoderLayer(embed_dim=256, d_ffn=512, n_heads=8, dropout=0.0,
+                                                   activation=torch.nn.ReLU(inplace=True), n_levels=4, n_points=4)
+        return rt.RelationTransformerDecoder(decoder_layer=layer, num_layers=3, num_classes=91)
+
+    ref, ours = _pair(build)
+    assert isinstance(ours.position_relation_embedding, modules.PositionRelationEmbedding)
+    with torch.no_grad():
+        for m in (ref, ours):
+            torch.manual_seed(1)
+            for layer in m.layers:
+                layer.cross_attn.sampling_offsets.weight.normal_(0, 0.02)
+                layer.cross_attn.attention_weights.weight.normal_(0, 0.05)
+            for head in m.bbox_head:  # zero-initialised upstream: every layer would see identical boxes
+                head.layers[-1].weight.normal_(0, 0.02)
+    ss, lsi = workloads.shape_tensors(LEVELS, DEV)
+    S = int(ss.prod(1).sum())
+    g = torch.Generator(device=DEV).manual_seed(5)
+    N, dn = 120, 40
+    query = torch.randn((2, N, 256), device=DEV, generator=g)
+    refpts = torch.cat([torch.rand((2, N, 2), device=DEV, generator=g) * 0.8 + 0.1,
+                        torch.rand((2, N, 2), device=DEV, generator=g) * 0.3 + 0.05], -1)
+    value = torch.randn((2, S, 256), device=DEV, generator=g)
+    valid = torch.ones((2, 4, 2), device=DEV)
+    attn_mask = workloads.cdn_attn_mask(N - dn, 10, 4, DEV)
+    wts = [torch.randn((2, N, 91), device=DEV, generator=g) for _ in range(3)]
+    wbs = [torch.randn((2, N, 4), device=DEV, generator=g) for _ in range(3)]
+    outs = []
+    for m in (ref, ours):
+        cls, box = m(query=query, reference_points=refpts, value=value, spatial_shapes=ss, level_start_index=lsi,
+                     valid_ratios=valid, key_padding_mask=None, attn_mask=attn_mask)
+        loss = sum((c * w).sum() for c, w in zip(cls, wts)) + sum((b * w).sum() for b, w in zip(box, wbs))
+        loss.backward()
+        outs.append((torch.stack(list(cls)).detach(), torch.stack(list(box)).detach()))
+    _assert_close(outs[1][0], outs[0][0], 5e-5, "decoder class logits")
+    _assert_close(outs[1][1], outs[0][1], 5e-5, "decoder boxes")
+    gr, go_ = _grads(ref), _grads(ours)
+    assert gr.keys() == go_.keys() and "position_relation_embedding.pos_proj.0.weight" in gr
+    for n in gr:
+        _assert_close(go_[n], gr[n], 5e-4, f"grad {n}")
+
+
+def test_relation_detr_loss_dict_matches_the_unmodified_reference():
+    """RelationDETR R50 (2 encoder / 2 decoder layers to bound the run time, everything else the shipped config) in
+    training mode on a seeded synthetic batch: every entry of the loss dict, with and without the B200 operators
+    and the device matcher."""
+    refmodel.activate()
+    rinstall.uninstall()
+    torch.manual_seed(0)
+    ref, _ = refmodel.build_relation_detr_r50(enc_layers=2, dec_layers=2)
+    rinstall.install()
+    torch.manual_seed(0)
+    ours, _ = refmodel.build_relation_detr_r50(enc_layers=2, dec_layers=2)
+    rinstall.uninstall()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ref, ours = ref.to(DEV).train(), ours.to(DEV).train()
+    from relation_detr_b200 import matcher as rmatcher
+    assert isinstance(ours.criterion.matcher, rmatcher.HungarianMatcher) and not isinstance(ref.criterion.matcher, rmatcher.HungarianMatcher)
+    images, targets = refmodel.synthetic_batch(2, DEV, seed=0, height=416, width=544, boxes_per_image=6)
+    losses = []
+    for m in (ref, ours):
+        torch.manual_seed(123)  # the denoising generator draws its noise from the global RNG
+        ld = m(copy.deepcopy(images), copy.deepcopy(targets))
+        sum(ld.values()).backward()
+        losses.append({k: v.detach().double().item() for k, v in ld.items()})
+    assert losses[0].keys() == losses[1].keys() and len(losses[0]) >= 24
+    worst = max(abs(losses[0][k] - losses[1][k]) / max(abs(losses[0][k]), 1e-6) for k in losses[0])
+    assert worst <= 2e-3, {k: (losses[0][k], losses[1][k]) for k in losses[0]}
+    g_ref = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+    g_our = {n: p.grad for n, p in ours.named_parameters() if p.grad is not None}
+    assert g_ref.keys() == g_our.keys()
+    num = sum(((g_our[n].double() - g_ref[n].double()) ** 2).sum() for n in g_ref).sqrt().item()
+    den = sum((g_ref[n].double() ** 2).sum() for n in g_ref).sqrt().item()
+    assert num / den <= 5e-3, num / den
