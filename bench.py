@@ -11,10 +11,16 @@ collective on the data path => weak scaling); the value is all ranks' algorithmi
 slowest rank's time.
 
 One JSON line on stdout (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (backward), algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores
-  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
-  extra         the other measured variants (loc distributions, bf16, decoder shapes, relation op, one step of bipartite matching)
+  roofline      dominant kernel (backward), algorithmic bytes / CUDA-event time vs measured HBM peak; `rel` = the fused
+                relation-bias kernels against their own bound (fp32 issue), `traffic` from the recorded ncu capture
+  cpu_baseline  the oracle port of the reference's CPU path timed on this box's host cores (same sample definition as
+                --impl reference), plus the whole reference model's CPU inference (BASELINE configs[0])
+  e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside), against the PCIe
+                rate measured with all ranks copying at once
+  train         the other half of BASELINE's metric: Relation-DETR R50 800x1333 training step, batch 2 per GPU, DDP/NCCL,
+                the reference's own model classes with the B200 operators installed (fp32 and bf16 autocast)
+  extra         the other measured variants (loc distributions, bf16, decoder shapes, relation op, matching, the same model
+                through the unmodified reference path, GPU-side reference baselines)
 """
 from __future__ import annotations
 
@@ -35,7 +41,17 @@ METRIC = "MSDeformAttn fwd+bwd GB/s"
 UNIT = "GB/s"
 WORKLOAD = "msda_enc_800x1333_b8"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
-NCU_BWD_DRAM_BYTES = 1_287_700_000  # 851.5 MB read + 436.3 MB written (profiles/r01d_ncu_summary.md), vs 1 097.2 MB algorithmic
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")  # written by tools/record_traffic.py from an ncu capture
+
+
+def recorded_traffic():
+    """DRAM bytes per backward call (kernel + the grad_value zero-fill) from the committed ncu capture, with the
+    commit it was taken at; None when no capture is recorded."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -137,6 +153,12 @@ def time_cpu_port(steps: int, warmup: int, sample_batch: int = 1, loc_kind: str 
     return (fwd + bwd) / dt / 1e9, dt * 1e3, cores, f"batch {sample_batch} of {WORKLOAD} ({sample_batch}/{full.batch} of one step), loc {loc_kind}, fp32, {steps} timed passes"
 
 
+def workloads_batch() -> int:
+    from relation_detr_b200 import workloads
+
+    return workloads.MSDA_SHAPES[WORKLOAD].batch
+
+
 def time_cpu_rel(steps: int = 3, batch: int = 2, n: int = 900):
     """The reference's eager relation embedding (oracle/torch_port.py, fwd + autograd bwd) on the host cores, as a
     second CPU baseline next to the MSDA one (BASELINE.json configs[2], bounded sample: `batch` of 8 images)."""
@@ -168,14 +190,15 @@ def run_reference(args):
         return 0
     import torch
 
-    steps = max(1, min(args.steps, 5))
-    warmup = max(1, min(args.warmup, 2))
-    gbs, ms, cores, sample = time_cpu_port(steps, warmup, 1, args.loc)
+    # same workload as our arm (batch 8) and the requested step counts: ~2-3 s per pass on the box's cores
+    steps, warmup = args.steps, args.warmup
+    gbs, ms, cores, sample = time_cpu_port(steps, warmup, workloads_batch(), args.loc)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "loc": args.loc, "note": "reference CPU path (grid_sample + autograd) via oracle/torch_port.py; each step = bounded sample"},
+        "config": {"workload": WORKLOAD, "loc": args.loc, "batch_per_gpu": workloads_batch(),
+                   "note": "reference CPU path (grid_sample + autograd) via oracle/torch_port.py on all host threads; each step = one full batch-8 pass"},
         "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "torch_threads": cores, "host_cpus": len(os.sched_getaffinity(0)),
@@ -362,6 +385,108 @@ def time_rel(torch, ops, wl, name, steps, warmup, fast):
     return {"fwd_ms": round(fwd, 4), "bwd_ms": round(bwd, 4), "fwd_GBps": round(fb / fwd / 1e6, 1), "bwd_GBps": round(bb / bwd / 1e6, 1)}
 
 
+
+def measure_pcie(torch, rdist, dev, mbytes: int = 256, reps: int = 4):
+    """Pinned host <-> device copy rate of THIS rank while every rank copies at the same time (barrier first), so that
+    at N > 1 the number is the host's shared ceiling, not one link's: GB/s per direction (both directions at once, as
+    the pipelined e2e path uses them), min over ranks."""
+    n = mbytes << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.zeros(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        torch.cuda.synchronize()
+        rdist.barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        for _ in range(reps + 1):
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        e1.record(s1)
+        e2.record(s2)
+        torch.cuda.synchronize()
+        ms = max(e0.elapsed_time(e1), e0.elapsed_time(e2))
+        gbs = n * (reps + 1) / ms / 1e6
+        res[mode] = round(-rdist.max_over_ranks(-gbs, dev), 2)  # min over ranks
+    return {"h2d_gbs": res["h2d"], "d2h_gbs": res["d2h"], "duplex_gbs_per_direction": res["both"], "buffer_MB": mbytes,
+            "how": "pinned 256 MB copies with CUDA events, every rank copying at the same time; min over ranks"}
+
+
+def gpu_side_baselines(torch, ops, wl, inp, steps):
+    """The reference's own implementations on the same GPU and inputs (guarded: needs oracle/_ref for its CUDA kernel):
+    (a) its grid_sample path (what upstream effectively runs on this image), (b) its CUDA kernel recompiled for sm_100a."""
+    from oracle import build_ref_cuda, torch_port
+
+    v, ss, lsi = inp["value"], inp["spatial_shapes"], inp["level_start_index"]
+    loc, attn, go = inp["sampling_locations"], inp["attention_weights"], inp["grad_output"]
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def port_fwd_bwd():
+        vv, ll, aa = v.detach().requires_grad_(True), loc.detach().requires_grad_(True), attn.detach().requires_grad_(True)
+        torch_port.msda_grid_sample(vv, ss, ll, aa).backward(go)
+
+    out = {"grid_sample_gpu": {"fwd_bwd_ms": round(timed(port_fwd_bwd, 3), 3)}}
+    refc = build_ref_cuda.load_prebuilt()
+    if refc is None:
+        out["ref_cuda_sm100a"] = {"unavailable": "oracle/_ref not built"}
+    else:
+        f = timed(lambda: refc.ms_deform_attn_forward(v, ss, lsi, loc, attn, 64), steps)
+        b = timed(lambda: refc.ms_deform_attn_backward(v, ss, lsi, loc, attn, go, 64), steps)
+        out["ref_cuda_sm100a"] = {"fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "fwd_bwd_ms": round(f + b, 4)}
+    return out
+
+
+def run_train_block(args, world, rank, quick: bool):
+    """BASELINE configs[3] on the real model (baseline/train_bench.py).  Every rank takes part (DDP); rank 0 keeps the result."""
+    from baseline import refmodel, train_bench
+
+    if not refmodel.available():
+        return {"unavailable": "baseline/_ref (the reference tree) is not installed: run python baseline/install_reference.py"}, {}
+    k = max(3, min(args.steps, 10))
+    train = {"model": "Relation-DETR ResNet-50 (reference classes from baseline/_ref, random init), 800x1333, batch 2 per GPU, "
+                      "AdamW + clip 0.1, DDP/NCCL gradient all-reduce" if world > 1 else
+                      "Relation-DETR ResNet-50 (reference classes from baseline/_ref, random init), 800x1333, batch 2, AdamW + clip 0.1",
+             "data": "synthetic images and 10 boxes per image", "operators": "relation_detr_b200.install.install(): MSDA (fused prologue), relation bias, device matcher"}
+    extra = {}
+    for prec in ("fp32", "bf16"):
+        try:
+            train[prec] = train_bench.run("ours", prec, k, 3, profile_share=(world == 1 and not quick))
+        except Exception as e:  # noqa: BLE001
+            train[prec] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if "imgs_per_s" in train.get("fp32", {}):
+        train["imgs_per_s"] = train["fp32"]["imgs_per_s"]
+        train["ms_per_step"] = train["fp32"]["ms_per_step"]
+    if "imgs_per_s" in train.get("bf16", {}):
+        train["imgs_per_s_bf16"] = train["bf16"]["imgs_per_s"]
+    if not quick:
+        for key, path, prec in (("train_reference_path", "reference", "fp32"), ("train_reference_path_bf16", "reference", "bf16"),
+                                ("train_reference_cuda_kernel", "reference_cuda", "fp32")):
+            try:
+                extra[key] = train_bench.run(path, prec, max(3, k // 2), 2)
+            except Exception as e:  # noqa: BLE001
+                extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return train, extra
+
+
 def run_ours(args):
     import torch
 
@@ -404,6 +529,10 @@ def run_ours(args):
     e2e_ms, h2d, d2h = time_e2e(torch, rd, inp, e2e_steps, 2)
     e2e_ms_max = rdist.max_over_ranks(e2e_ms, dev)
     e2e_value = world * (fwd_b + bwd_b) / e2e_ms_max / 1e6
+    try:
+        pcie = measure_pcie(torch, rdist, dev)
+    except Exception as e:  # noqa: BLE001  (diagnostic only)
+        pcie = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     extra = {}
     cpu_baseline = None
@@ -442,14 +571,38 @@ def run_ours(args):
             guarded(name + "_exact", lambda name=name: time_rel(torch, ops, workloads, name, k, w, False))
             guarded(name + "_fast", lambda name=name: time_rel(torch, ops, workloads, name, k, w, True))
         guarded("matching_step_b2", lambda: time_matching(torch, rd, k, w))
+        guarded("gpu_baselines", lambda: gpu_side_baselines(torch, ops, workloads, inp, k))
     if rank == 0 and not args.no_cpu_baseline:
-        gbs, cms, cores, sample = time_cpu_port(8, 2, 2, args.loc)  # ~10 s of host work on the GPU box
+        # the same sample as one step of `--impl reference` (a full batch-8 pass), 1 warm-up + 3 timed: ~10 s of host work
+        gbs, cms, cores, sample = time_cpu_port(3, 1, shape.batch, args.loc)
         cpu_baseline = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_sample": round(cms, 2)}
         try:
             cpu_baseline["relation"] = time_cpu_rel()
         except Exception as e:  # noqa: BLE001
             cpu_baseline["relation"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        try:  # BASELINE configs[0]: the whole reference model on the host cores
+            from baseline import refmodel, train_bench
+            cpu_baseline["whole_model"] = train_bench.cpu_inference(3) if refmodel.available() else {"unavailable": "baseline/_ref not installed"}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline["whole_model"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    traffic = recorded_traffic()
+    # the other half of the metric: the real model's training step (all ranks take part)
+    train, train_extra = ({"skipped": "--no-train"}, {}) if args.no_train else run_train_block(args, world, rank, args.quick)
+    extra.update(train_extra)
+    rel_roof = None
+    if rank == 0 and "rel_900_b8_fast" in extra and "fwd_ms" in extra["rel_900_b8_fast"]:
+        r = extra["rel_900_b8_fast"]
+        rb = workloads.REL_SHAPES["rel_900_b8"].algorithmic_bytes()
+        pairs = 8 * 900 * 900
+        fma_floor_us = pairs * 512 / (148 * 128 * 1.965e9) * 1e6  # 64->8 projection alone on the FP32 pipe
+        rel_roof = {"workload": "rel_900_b8 (B=8, N=900, H=8), FAST mode", "bound": "fp32-issue",
+                    "fwd": {"ms": r["fwd_ms"], "achieved": r["fwd_GBps"], "frac": round(r["fwd_GBps"] / peak, 4)},
+                    "bwd": {"ms": r["bwd_ms"], "achieved": r["bwd_GBps"], "frac": round(r["bwd_GBps"] / peak, 4)},
+                    "unit": "GB/s", "peak": peak, "algorithmic_bytes": {"fwd": rb[0], "bwd": rb[1]},
+                    "fma_floor_us": round(fma_floor_us, 1), "fwd_over_fma_floor": round(r["fwd_ms"] * 1e3 / fma_floor_us, 2),
+                    "note": "32 B of output per box pair against 512 FMA + 32 sin/cos: the FP32 pipe, not HBM, is the roofline; "
+                            "frac is quoted against HBM only because BASELINE.json asks for it"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -460,11 +613,11 @@ def run_ours(args):
                        "l2": "inputs (640 MB fwd / 1097 MB bwd) exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "msda_bwd_kernel<float,32> (+ grad_value zero-fill memset, both inside rdetr_msda_backward)",
                          "achieved": round(bwd_b / bwd_max / 1e6, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(bwd_b / bwd_max / 1e6 / peak, 4), "traffic": NCU_BWD_DRAM_BYTES if args.loc == "S" else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of msda_bwd_kernel per launch, ncu --set full, profiles/r01d_ncu_summary.md (loc S)",
+                         "frac": round(bwd_b / bwd_max / 1e6 / peak, 4), "traffic": (traffic or {}).get("dram_bytes_per_call") if args.loc == "S" else None,
+                         "traffic_source": traffic,
                          "algorithmic_bytes": bwd_b, "peak_source": peak_src,
                          "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
-                         "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4),
+                         "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4), "rel": rel_roof,
                          # the resources that actually bind: one 128-byte row per bilinear corner
                          "binding": {
                              "corner_rows_per_launch": corner_rows,
@@ -476,7 +629,14 @@ def run_ours(args):
                              "note": "fwd is bound by the L1 gather path (one 128-byte wavefront per corner row; latency-limited below the measured ceiling), bwd by the L2 atomic unit; neither can reach the HBM roofline with the reference's [B,S,M,D] layout"}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "hostpipe.MsdaHostPipeline (MultiScaleDeformableAttnFunction.apply + autograd), pinned host buffers, copies overlapped across steps"},
+                    "ms_per_step": round(e2e_ms_max, 3), "steps": e2e_steps, "api": "hostpipe.MsdaHostPipeline (MultiScaleDeformableAttnFunction.apply + autograd), pinned host buffers, copies overlapped across steps",
+                    "pcie_peak_gbs": pcie,
+                    # the pipelined path moves h2d and d2h bytes concurrently: its ceiling is the duplex per-direction rate
+                    "copy_gbs_per_direction": round(max(h2d, d2h) / e2e_ms_max / 1e6, 2),
+                    "frac_of_pcie": (round(max(h2d, d2h) / e2e_ms_max / 1e6 / pcie["duplex_gbs_per_direction"], 3)
+                                     if isinstance(pcie, dict) and pcie.get("duplex_gbs_per_direction") else None),
+                    "bound": "host <-> device copies (640 MB each way per step), not the kernels"},
+            "train": train,
             "gpu_launches": 2 * args.steps, "clocks": clocks, "extra": extra,
         }
         emit(line)
@@ -522,6 +682,7 @@ def main():
     ap.add_argument("--loc", choices=["S", "U"], default="S", help="sampling-location distribution (S = encoder-realistic, U = uniform)")
     ap.add_argument("--quick", action="store_true", help="skip the extra variants")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the whole-model training block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

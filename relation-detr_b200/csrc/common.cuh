@@ -184,7 +184,11 @@ struct Tap {
     float lw, lh;
 };
 
-__device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int start)
+// `S` = rows of one image's value tensor: a corner whose pixel index reaches S (spatial_shapes / level_start_index
+// inconsistent with the value tensor the caller passed) is treated as padding instead of being dereferenced -- the
+// reference asserts the sizes on the host with a device sync per call (ms_deform_attn.py:313), which the drop-in
+// module does not do.
+__device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int start, int S = 0x7fffffff)
 {
     Tap t;
     const float w_im = fmaf(lx, (float)W, -0.5f);
@@ -202,6 +206,11 @@ __device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int st
     t.pix[1] = (h0ok && w1ok) ? base + 1 : -1;
     t.pix[2] = (h1ok && w0ok) ? base + W : -1;
     t.pix[3] = (h1ok && w1ok) ? base + W + 1 : -1;
+    if (base + W + 1 >= S || start < 0) {  // only with inconsistent shape tensors
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (t.pix[i] >= S || start < 0) t.pix[i] = -1;
+    }
     if (!inside) { t.lh = 0.f; t.lw = 0.f; }  // NaN / inf locations must not leak into weights
     return t;
 }
@@ -335,7 +344,7 @@ __device__ __forceinline__ Tap sample_tap(const IO &io, long long pair0, int s, 
         xy = ld_stream_f2(reinterpret_cast<const float2 *>(io.loc) + pair0 * LP + s);
         a = ld_stream_f1(io.attn + pair0 * LP + s);
     }
-    Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l]);
+    Tap t = make_tap(xy.x, xy.y, s_H[l], s_W[l], s_start[l], S);
     if constexpr (IO::kFused) {
         if (io.mask != nullptr) {
             const uint8_t *mrow = io.mask + (long long)s_b[pair] * S;

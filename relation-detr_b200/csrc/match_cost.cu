@@ -70,6 +70,12 @@ match_cost_kernel(const __grid_constant__ CostLaunch launch, const CostParams pr
         const long long label = __ldg(task.gt_labels + g);
 
         // classification: focal-style cost of the target's class
+        // a label outside [0, num_classes) would be an out-of-bounds read (the reference's advanced indexing raises a
+        // device-side assert): poison the cost instead, so that rdetr_lsap_solve reports status 2 for the problem
+        if (label < 0 || label >= prm.num_classes) {
+            task.cost[e] = __int_as_float(0x7fc00000);
+            continue;
+        }
         const float x = __ldg(task.pred_logits + (size_t)q * prm.num_classes + label);
         const float p = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
         const float omp = __fsub_rn(1.0f, p);

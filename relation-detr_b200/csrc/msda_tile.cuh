@@ -186,6 +186,13 @@ __device__ __forceinline__ void tile_phase1(const IO &io, const TileGeom &geo, i
         if (live) {
             const int H = geo.H[l], W = geo.W[l];
             TapHW t = make_tap_hw(xy.x, xy.y, H, W);
+            if (t.vm && (geo.start[l] < 0 || geo.start[l] + (t.h0 + 1) * W + t.w0 + 1 >= S)) {  // inconsistent shape tensors only
+                const int p00 = geo.start[l] + t.h0 * W + t.w0;
+                if (geo.start[l] < 0 || p00 >= S) t.vm &= ~1u;
+                if (geo.start[l] < 0 || p00 + 1 >= S) t.vm &= ~2u;
+                if (geo.start[l] < 0 || p00 + W >= S) t.vm &= ~4u;
+                if (geo.start[l] < 0 || p00 + W + 1 >= S) t.vm &= ~8u;
+            }
             if constexpr (IO::kFused) {
                 if (io.mask != nullptr && t.vm) {
                     const uint8_t *mrow = io.mask + (long long)b * S + geo.start[l] + t.h0 * W + t.w0;

@@ -341,9 +341,11 @@ rel_fwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
                 unpack2(acc[r >> 1][h], lo, hi);
                 const float a = (r & 1) ? hi : lo;
 #endif
-                const bool pos = jok && a > 0.f;
+                // a blocked (masked_fill -inf) position gets no gradient, whatever the caller feeds back there:
+                // the reference's masked_fill_ cuts the graph at those elements (relation_transformer.py:372-374)
+                const bool pos = jok && !blocked && a > 0.f;
                 words[h] = __ballot_sync(0xffffffffu, pos);
-                if (jok) out[(((size_t)b * kRelHeads + h) * N1 + i) * N2 + j] = blocked ? -INFINITY : (pos ? a : 0.f);
+                if (jok) out[(((size_t)b * kRelHeads + h) * N1 + i) * N2 + j] = blocked ? -INFINITY : (a > 0.f ? a : 0.f);
             }
             if (relu_bits != nullptr && lane == 0) {
                 uint4 *dst = reinterpret_cast<uint4 *>(relu_bits + (((size_t)b * N1 + i) * nwords + blockIdx.x) * kRelHeads);

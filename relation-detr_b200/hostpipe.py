@@ -38,14 +38,17 @@ class MsdaHostPipeline:
 
     def submit(self, host: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Enqueue one step on pinned host tensors (keys: value, sampling_locations, attention_weights,
-        grad_output).  Returns the pinned host tensors the results will land in; they are valid after
-        ``wait()`` (or after ``depth`` further submits)."""
+        grad_output).  Returns the pinned host tensors the results will land in.  They are valid after ``wait()``
+        and are OVERWRITTEN by the ``depth``-th submit that follows: consume (or copy) them before resubmitting
+        that slot."""
         i = self.step_index
         b = i % self.depth
         self.step_index += 1
         with torch.cuda.stream(self.s_in):
             if self.dev_in[b] is None:
                 self.dev_in[b] = {k: torch.empty(host[k].shape, dtype=host[k].dtype, device=self.device) for k in _IN_KEYS}
+                for t in self.dev_in[b].values():  # allocated under s_in, read by the kernels on s_compute: keep the
+                    t.record_stream(self.s_compute)  # caching allocator from recycling the block while compute is pending
             else:
                 self.s_in.wait_event(self.ev_compute_done[b])  # step i-depth has finished reading this buffer
             for k in _IN_KEYS:

@@ -70,6 +70,9 @@ class HungarianMatcher(nn.Module):
         self.check_status = check_status
         self.fused_cost = fused_cost
         self.last_status = None
+        self._flag_host = None
+        self._flag_event = None
+        self._flag_pending = False
 
     # -- cost terms: hungarian_matcher.py:40-72, same operations in the same order -----------------------
     def calculate_class_cost(self, pred_logits, gt_labels, **kwargs):
@@ -112,6 +115,7 @@ class HungarianMatcher(nn.Module):
         return src_ind[ind].view(-1), tgt_ind
 
     def _solve(self, mats: Sequence[Tensor]):
+        self._raise_deferred()
         pairs, status = ops.lsap_solve(mats)
         self.last_status = status
         if self.check_status:
@@ -119,7 +123,36 @@ class HungarianMatcher(nn.Module):
             if bad:
                 code = int(status[bad[0]])
                 raise ValueError("cost matrix is infeasible" if code == 1 else "matrix contains invalid numeric entries")
+        elif status.numel():
+            # Failures must not stay silent (SciPy raises ValueError; a failed problem here returns -1 indices, which
+            # the criterion would use as "last query / last target"), but a check per call would put a host sync back
+            # into every decoder layer.  Deferred check: the worst status code travels to pinned host memory behind an
+            # event, and the NEXT call (or ``check_deferred()``) raises once the copy has landed -- never blocking.
+            if self._flag_host is None:
+                self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+                self._flag_event = torch.cuda.Event()
+            self._flag_host.copy_(status.max().reshape(1), non_blocking=True)
+            self._flag_event.record()
+            self._flag_pending = True
         return pairs
+
+    def _raise_deferred(self, wait: bool = False) -> None:
+        if not self._flag_pending:
+            return
+        if wait:
+            self._flag_event.synchronize()
+        elif not self._flag_event.query():
+            return
+        self._flag_pending = False
+        code = int(self._flag_host[0])
+        if code:
+            raise ValueError(("cost matrix is infeasible" if code == 1 else "matrix contains invalid numeric entries")
+                             + " (reported by an earlier HungarianMatcher call; its indices were -1)")
+
+    def check_deferred(self) -> None:
+        """Blocks until the status of the most recent call is known and raises ``ValueError`` if a problem failed
+        (what SciPy raises at hungarian_matcher.py:80).  Call it once per step if failures must surface in-step."""
+        self._raise_deferred(wait=True)
 
     def _costs(self, pred_boxes, pred_logits, gt_boxes, gt_labels) -> List[Tensor]:
         """Cost matrices of a batch of problems: one fused launch (``rdetr_match_cost``, the eager chain's

@@ -200,3 +200,31 @@ def test_errors_are_raised_not_swallowed():
     bad = torch.full((4, 4), float("nan"), device=DEV)
     with pytest.raises(ValueError, match="invalid numeric"):
         m._solve([bad])
+
+
+def test_out_of_range_labels_poison_the_cost_and_failures_surface_without_a_sync_per_call():
+    """a target label outside [0, num_classes) must not become an out-of-bounds read, and a failed problem
+    must not stay silent.  The fused cost kernel writes NaN for such a column, the solver reports status 2, and the
+    matcher raises ValueError -- immediately with check_status=True, otherwise on the next call / check_deferred()."""
+    g = torch.Generator().manual_seed(0)
+    pb = torch.cat([torch.rand(50, 2, generator=g) * 0.8 + 0.1, torch.rand(50, 2, generator=g) * 0.3 + 0.02], -1).to(DEV)
+    pl = torch.randn(50, 80, generator=g).to(DEV)
+    gb = torch.cat([torch.rand(4, 2, generator=g) * 0.8 + 0.1, torch.rand(4, 2, generator=g) * 0.3 + 0.02], -1).to(DEV)
+    bad_labels = torch.tensor([3, 90, 7, 2], device=DEV)  # 90 >= 80 classes (COCO ids against an 80-class head)
+    cost = ops.match_cost([pb], [pl], [gb], [bad_labels], 2.0, 5.0, 2.0, 0.25, 2.0)[0]
+    assert torch.isnan(cost[:, 1]).all() and torch.isfinite(cost[:, [0, 2, 3]]).all()
+    with pytest.raises(ValueError, match="invalid numeric"):
+        rd.HungarianMatcher(2, 5, 2, check_status=True)(pb, pl, gb, bad_labels)
+    m = rd.HungarianMatcher(2, 5, 2)
+    src, tgt = m(pb, pl, gb, bad_labels)  # does not raise and does not synchronise ...
+    assert int(m.last_status[0]) == 2 and bool((src < 0).all())
+    with pytest.raises(ValueError, match="earlier HungarianMatcher call"):
+        m.check_deferred()  # ... but the failure is reported
+    good = torch.tensor([3, 9, 7, 2], device=DEV)
+    m(pb, pl, gb, bad_labels)
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError):
+        m(pb, pl, gb, good)  # the next call reports the earlier failure once its status has landed
+    src, tgt = m(pb, pl, gb, good)
+    m.check_deferred()
+    assert bool((src >= 0).all())

@@ -188,3 +188,25 @@ def test_focal_config_size_properties():
         assert torch.isfinite(w.grad).all() and w.grad.abs().sum() > 0
         w.grad = None
         b.grad = None
+
+
+def test_masked_positions_carry_no_gradient_whatever_the_upstream_gradient():
+    """with the fused -inf mask, a blocked position must not contribute to grad_weight / grad_bias even
+    when the caller's gradient is non-zero there -- the reference's masked_fill_ cuts the graph at those elements."""
+    r = workloads.make_rel_inputs(workloads.RelShape("t", 2, 70, 45), seed=3, device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    mask = torch.rand((70, 45), device=DEV, generator=g) > 0.6
+    go = torch.randn((2, 8, 70, 45), device=DEV, generator=g)  # deliberately non-zero at masked positions
+    for fast in (False, True):
+        w = r["weight"].clone().requires_grad_(True)
+        b = r["bias"].clone().requires_grad_(True)
+        out = ops.position_relation_bias(r["src_boxes"], r["tgt_boxes"], w, b, attn_mask=mask, fast=fast)
+        out.backward(go)
+        w64 = r["weight"].double().requires_grad_(True)
+        b64 = r["bias"].double().requires_grad_(True)
+        ref = torch_port.rel_eager(r["src_boxes"].double(), r["tgt_boxes"].double(), w64, b64)
+        ref = ref.masked_fill(mask, float("-inf"))  # out-of-place twin of relation_transformer.py:372-374
+        ref.backward(go.double())
+        assert torch.equal(torch.isneginf(out), mask[None, None].expand_as(out))
+        assert ((w.grad.double() - w64.grad).abs().max() / w64.grad.abs().max()).item() <= 5e-4
+        assert ((b.grad.double() - b64.grad).abs().max() / b64.grad.abs().max()).item() <= 5e-4
