@@ -175,6 +175,38 @@ int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, cons
                             size_t workspace_bytes, rdetr_stream_t stream);
 
 /*
+ * Decoder self-attention with the position-relation bias generated on the fly.
+ * Replaces, between nn.MultiheadAttention's input and output projections, the chain
+ *   PositionRelationEmbedding(src, tgt).flatten(0, 1) -> masked_fill_(attn_mask, -inf) -> attn_mask of the attention
+ * (upstream models/bricks/relation_transformer.py:369-374 producer, :453-459 consumer): the [B, H, N, N] bias and its
+ * gradient never exist in HBM on the forward path.
+ *   out[b,h,i,:] = sum_j softmax_j(q[b,h,i,:].k[b,h,j,:] / sqrt(D) + relu(weight[h,:].f(src_i, tgt_j) + bias[h])) v[b,h,j,:]
+ *
+ *   q, k, v     [B, H, N, D] fp32, contiguous, 16-byte aligned     out [B, H, N, D] fp32
+ *   src_boxes   [B, N, 4] boxes of the query rows, tgt_boxes [B, N, 4] boxes of the keys (fp32 cxcywh)
+ *   weight [H, 64], bias [H], dim_t [8] (device), scale, eps: as rdetr_relation_forward (FAST arithmetic only)
+ *   attn_mask   NULL or [N, N] bytes (torch.bool), non-zero = key j blocked for query i
+ *   lse         [B, H, N] fp32: log-sum-exp of every row, the only thing the backward needs besides the inputs and out
+ *   grad_q / grad_k / grad_v like q; grad_weight [H, 64], grad_bias [H]: all ZEROED INSIDE the backward call
+ *   workspace   rdetr_relation_attention_workspace_bytes(B, N, H, backward) bytes: per-box tables, plus -- backward only --
+ *               one [B, H, N, N] fp32 buffer through which the ReLU-gated score gradient reaches the relation backward
+ * Supported: H == 8, D == 32.  A row whose keys are all blocked yields NaN, as torch's softmax does.
+ */
+size_t rdetr_relation_attention_workspace_bytes(int B, int N, int H, int backward);
+int rdetr_relation_attention_forward(const float *q, const float *k, const float *v, const float *src_boxes,
+                                     const float *tgt_boxes, const float *weight, const float *bias,
+                                     const float *dim_t, float scale, float eps, const uint8_t *attn_mask,
+                                     float *out, float *lse, int B, int N, int H, int D, void *workspace,
+                                     size_t workspace_bytes, rdetr_stream_t stream);
+int rdetr_relation_attention_backward(const float *q, const float *k, const float *v, const float *src_boxes,
+                                      const float *tgt_boxes, const float *weight, const float *bias,
+                                      const float *dim_t, float scale, float eps, const uint8_t *attn_mask,
+                                      const float *out, const float *lse, const float *grad_out, float *grad_q,
+                                      float *grad_k, float *grad_v, float *grad_weight, float *grad_bias, int B,
+                                      int N, int H, int D, void *workspace, size_t workspace_bytes,
+                                      rdetr_stream_t stream);
+
+/*
  * Batched rectangular linear-sum-assignment.
  * Replaces scipy.optimize.linear_sum_assignment(c.cpu()) at models/matcher/hungarian_matcher.py:80 and :87
  * (one device->host copy + host solve per image and per decoder layer).  All problems of one call are

@@ -43,10 +43,27 @@ class InstallReport(list):
         self.skipped = list(skipped)
 
 
-def install(reference_root: str | None = None, strict: bool = True, matcher_too: bool = True) -> InstallReport:
+class _NNProxy:
+    """Stands in for the name ``nn`` inside ``models.bricks.relation_transformer`` (``from torch import nn``): every
+    attribute is ``torch.nn``'s except ``MultiheadAttention``, so that ``RelationTransformerDecoderLayer.__init__``
+    (``relation_transformer.py:401``) builds the fused self-attention without the file being edited."""
+
+    def __getattr__(self, name):
+        import torch.nn
+
+        if name == "MultiheadAttention":
+            return modules.RelationMultiheadAttention
+        return getattr(torch.nn, name)
+
+
+def install(reference_root: str | None = None, strict: bool = True, matcher_too: bool = True,
+            fused_attention: bool = False) -> InstallReport:
     """Returns the ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
     ``HungarianMatcher`` (device-resident matching): its index tensors are CUDA
-    tensors, which every use in ``models/bricks/set_criterion.py`` accepts."""
+    tensors, which every use in ``models/bricks/set_criterion.py`` accepts.  ``fused_attention`` (row N1) makes the
+    relation decoder's self-attention generate the position-relation bias inside the attention kernel:
+    ``PositionRelationEmbedding`` hands out a lazy handle and the decoder layer's ``nn.MultiheadAttention`` becomes
+    ``RelationMultiheadAttention`` (same parameters, same state-dict keys)."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     report = InstallReport()
@@ -82,6 +99,15 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
             report.skipped.append(f"{name} ({type(e).__name__}: {e})")
             continue
         rebind(mod, name, "HungarianMatcher", matcher.HungarianMatcher)
+    if fused_attention:
+        try:
+            mod = importlib.import_module("models.bricks.relation_transformer")
+        except Exception as e:
+            raise RuntimeError(f"relation_detr_b200.install: cannot import models.bricks.relation_transformer ({type(e).__name__}: {e})") from e
+        rebind(mod, "models.bricks.relation_transformer", "nn", _NNProxy())
+        if "PositionRelationEmbedding.lazy" not in _saved:
+            _saved["PositionRelationEmbedding.lazy"] = modules.PositionRelationEmbedding.lazy
+        modules.PositionRelationEmbedding.lazy = True
     if strict and not report:
         raise RuntimeError("relation_detr_b200.install: no name of the reference was rebound")
     return report
@@ -90,6 +116,8 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
 def uninstall() -> list:
     """Puts the reference's own classes back (models built in between keep whatever they were built with)."""
     restored = []
+    if "PositionRelationEmbedding.lazy" in _saved:
+        modules.PositionRelationEmbedding.lazy = _saved.pop("PositionRelationEmbedding.lazy")
     for key, obj in list(_saved.items()):
         name, attr = key.rsplit(".", 1)
         mod = sys.modules.get(name)

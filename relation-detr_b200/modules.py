@@ -148,7 +148,11 @@ class PositionRelationEmbedding(nn.Module):
             self._dim_t[key] = ops.relation_dim_t(self.embed_dim, self.temperature, device)
         return self._dim_t[key]
 
-    def forward(self, src_boxes: Tensor, tgt_boxes: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None) -> Tensor:
+    #: set by ``install(fused_attention=True)``: ``forward`` then returns a ``LazyRelationBias`` handle that
+    #: ``RelationMultiheadAttention`` turns into one fused kernel (row N1); any other consumer materialises it.
+    lazy = False
+
+    def forward(self, src_boxes: Tensor, tgt_boxes: Optional[Tensor] = None, attn_mask: Optional[Tensor] = None):
         """src_boxes [B,N1,4], tgt_boxes [B,N2,4] (default: src) -> [B,H,N1,N2], a fresh tensor the
         caller may mutate.  ``attn_mask`` ([N1,N2] bool, optional, not in the reference signature)
         fuses the decoder's ``masked_fill_(attn_mask, -inf)``."""
@@ -156,9 +160,90 @@ class PositionRelationEmbedding(nn.Module):
             tgt_boxes = src_boxes
         torch._assert(src_boxes.shape[-1] == 4, "src_boxes much have 4 coordinates")
         torch._assert(tgt_boxes.shape[-1] == 4, "tgt_boxes must have 4 coordinates")
+        if self.lazy and attn_mask is None and src_boxes.shape[1] == tgt_boxes.shape[1] and self.fast_math:
+            return LazyRelationBias(self, src_boxes, tgt_boxes)
+        return self._materialize(src_boxes, tgt_boxes, attn_mask)
+
+    def _materialize(self, src_boxes: Tensor, tgt_boxes: Tensor, attn_mask: Optional[Tensor]) -> Tensor:
         conv = self.pos_proj[0]
         out = ops.position_relation_bias(src_boxes, tgt_boxes, conv.weight, conv.bias, self._dim_t_on(src_boxes.device),
                                          self.scale, self.eps, attn_mask, self.fast_math)
         if torch.is_autocast_enabled():
             out = out.to(torch.get_autocast_dtype("cuda"))  # the reference's Conv2d returns the autocast dtype
         return out
+
+
+class LazyRelationBias:
+    """What ``PositionRelationEmbedding`` returns when the fused relation attention is installed: the boxes and the
+    embedding's parameters, not the ``[B, H, N, N]`` tensor.  It answers the two calls the reference's decoder makes on the
+    tensor (``relation_transformer.py:372-374``: ``.flatten(0, 1)`` and ``.masked_fill_(attn_mask, -inf)``) by recording
+    them; ``RelationMultiheadAttention`` consumes it in one kernel, and ``materialize()`` produces the real tensor
+    for any other consumer."""
+
+    def __init__(self, embedding: "PositionRelationEmbedding", src_boxes: Tensor, tgt_boxes: Tensor):
+        self.embedding = embedding
+        self.src_boxes = src_boxes
+        self.tgt_boxes = tgt_boxes
+        self.mask: Optional[Tensor] = None
+        self.flattened = False
+
+    def flatten(self, start_dim: int = 0, end_dim: int = -1):
+        if (start_dim, end_dim) != (0, 1):
+            return self.materialize().flatten(start_dim, end_dim)
+        self.flattened = True
+        return self
+
+    def masked_fill_(self, mask: Tensor, value):
+        if not (mask.dtype == torch.bool and mask.dim() == 2 and float(value) == float("-inf") and self.mask is None):
+            raise NotImplementedError("LazyRelationBias records one masked_fill_(bool [N, N] mask, -inf); materialize() it for anything else")
+        self.mask = mask.contiguous()
+        return self
+
+    @property
+    def shape(self):
+        B, N1, N2, H = self.src_boxes.shape[0], self.src_boxes.shape[1], self.tgt_boxes.shape[1], self.embedding.num_heads
+        return torch.Size((B * H, N1, N2)) if self.flattened else torch.Size((B, H, N1, N2))
+
+    def materialize(self) -> Tensor:
+        out = self.embedding._materialize(self.src_boxes, self.tgt_boxes, self.mask)
+        return out.flatten(0, 1) if self.flattened else out
+
+
+class RelationMultiheadAttention(nn.MultiheadAttention):
+    """``nn.MultiheadAttention`` (same parameters and state-dict keys) whose ``attn_mask`` may be a ``LazyRelationBias``:
+    the self-attention of ``RelationTransformerDecoderLayer`` (``relation_transformer.py:453-459``) then runs as
+    in-projection GEMMs -> ``rdetr::relation_attention_forward`` -> out-projection, and the relation bias is never written
+    to memory.  Every other call is ``nn.MultiheadAttention``'s own."""
+
+    def _fusable(self, query, key, value, key_padding_mask, need_weights) -> bool:
+        return (self.batch_first and self._qkv_same_embed_dim and self.in_proj_bias is not None and not need_weights
+                and key_padding_mask is None and self.bias_k is None and not self.add_zero_attn
+                and (self.dropout == 0.0 or not self.training) and query.dim() == 3 and key.shape == query.shape == value.shape
+                and self.num_heads == 8 and self.head_dim == 32 and query.is_cuda)
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None, average_attn_weights=True,
+                is_causal=False):
+        if not isinstance(attn_mask, LazyRelationBias):
+            return super().forward(query, key, value, key_padding_mask=key_padding_mask, need_weights=need_weights,
+                                   attn_mask=attn_mask, average_attn_weights=average_attn_weights, is_causal=is_causal)
+        rel = attn_mask
+        if not self._fusable(query, key, value, key_padding_mask, need_weights) or rel.src_boxes.shape[1] != query.shape[1]:
+            return super().forward(query, key, value, key_padding_mask=key_padding_mask, need_weights=need_weights,
+                                   attn_mask=rel.materialize(), average_attn_weights=average_attn_weights, is_causal=is_causal)
+        B, N, E = query.shape
+        H, D = self.num_heads, self.head_dim
+        w, b = self.in_proj_weight, self.in_proj_bias
+        if key is query:
+            qk = torch.nn.functional.linear(query, w[:2 * E], b[:2 * E])
+            q, k = qk[..., :E], qk[..., E:]
+        else:
+            q = torch.nn.functional.linear(query, w[:E], b[:E])
+            k = torch.nn.functional.linear(key, w[E:2 * E], b[E:2 * E])
+        v = torch.nn.functional.linear(value, w[2 * E:], b[2 * E:])
+        heads = lambda t: t.view(B, N, H, D).transpose(1, 2)  # noqa: E731  ([B, H, N, D]; made contiguous fp32 by the op wrapper)
+        emb = rel.embedding
+        conv = emb.pos_proj[0]
+        core = ops.relation_attention(heads(q), heads(k), heads(v), rel.src_boxes, rel.tgt_boxes, conv.weight, conv.bias,
+                                      emb._dim_t_on(query.device), emb.scale, emb.eps, rel.mask)
+        core = core.transpose(1, 2).reshape(B, N, E).to(q.dtype)
+        return self.out_proj(core), None

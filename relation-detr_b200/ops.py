@@ -24,6 +24,7 @@ from . import _lib
 __all__ = [
     "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
     "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
+    "relation_attention_forward", "relation_attention_backward", "relation_attention",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
     "lsap_solve", "match_cost",
 ]
@@ -359,6 +360,108 @@ def position_relation_bias(src_boxes: Tensor, tgt_boxes: Optional[Tensor], weigh
         dim_t = relation_dim_t(16, 10000.0, src_boxes.device)
     out, _ = relation_forward(src_boxes.detach().float().contiguous(), tgt_boxes.detach().float().contiguous(),
                               weight.float().contiguous(), bias.float().contiguous(), dim_t, scale, eps, attn_mask, fast)
+    return out
+
+
+# ---- fused relation attention -----------------------------------------
+
+def _check_relattn(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, attn_mask):
+    for name, t in (("q", q), ("k", k), ("v", v), ("src_boxes", src_boxes), ("tgt_boxes", tgt_boxes), ("weight", weight),
+                    ("bias", bias), ("dim_t", dim_t)):
+        _require(t.is_cuda, f"{name} must be a CUDA tensor")
+        _require(t.dtype == torch.float32, f"{name} must be float32")
+        _require(t.is_contiguous(), f"{name} tensor has to be contiguous")
+    _require(q.dim() == 4 and q.shape == k.shape == v.shape, "q, k, v must be [B, H, N, D] of one shape")
+    B, H, N, D = q.shape
+    _require(src_boxes.shape == (B, N, 4) and tgt_boxes.shape == (B, N, 4), "boxes must be [B, N, 4]")
+    _require(weight.numel() == H * 64 and bias.numel() == H and dim_t.numel() == 8, "weight must hold [H, 64] values, bias H, dim_t 8")
+    if attn_mask is not None:
+        _require(attn_mask.is_cuda and attn_mask.dtype == torch.bool and attn_mask.is_contiguous() and attn_mask.shape == (N, N),
+                 "attn_mask must be a contiguous CUDA bool tensor of shape [N, N]")
+    return B, H, N, D
+
+
+@torch.library.custom_op("rdetr::relation_attention_forward", mutates_args=(), device_types="cuda")
+def relation_attention_forward(q: Tensor, k: Tensor, v: Tensor, src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias: Tensor,
+                               dim_t: Tensor, scale: float, eps: float, attn_mask: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    B, H, N, D = _check_relattn(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, attn_mask)
+    out = torch.empty_like(q)
+    lse = torch.empty((B, H, N), dtype=torch.float32, device=q.device)
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_relation_attention_workspace_bytes(B, N, H, 0)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device) if ws_bytes else None
+    with torch.cuda.device(q.device):
+        rc = L_.rdetr_relation_attention_forward(_ptr(q), _ptr(k), _ptr(v), _ptr(src_boxes), _ptr(tgt_boxes), _ptr(weight), _ptr(bias),
+                                                 _ptr(dim_t), float(scale), float(eps), _ptr(attn_mask), _ptr(out), _ptr(lse),
+                                                 B, N, H, D, _ptr(ws), ws_bytes, _stream(q))
+    _lib.check(rc, "rdetr_relation_attention_forward")
+    return out, lse
+
+
+@relation_attention_forward.register_fake
+def _(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask):
+    return torch.empty_like(q), q.new_empty(q.shape[:3])
+
+
+@torch.library.custom_op("rdetr::relation_attention_backward", mutates_args=(), device_types="cuda")
+def relation_attention_backward(q: Tensor, k: Tensor, v: Tensor, src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias: Tensor,
+                                dim_t: Tensor, scale: float, eps: float, attn_mask: Optional[Tensor], out: Tensor, lse: Tensor,
+                                grad_out: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    B, H, N, D = _check_relattn(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, attn_mask)
+    grad_out = grad_out.to(torch.float32).contiguous()
+    _require(grad_out.shape == q.shape, "grad_out must have the shape of q")
+    gq, gk, gv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)   # gk / gv are zeroed inside the library
+    gw = torch.empty((H, 64), dtype=torch.float32, device=q.device)
+    gb = torch.empty((H,), dtype=torch.float32, device=q.device)
+    L_ = _lib.lib()
+    ws_bytes = L_.rdetr_relation_attention_workspace_bytes(B, N, H, 1)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=q.device) if ws_bytes else None
+    with torch.cuda.device(q.device):
+        rc = L_.rdetr_relation_attention_backward(_ptr(q), _ptr(k), _ptr(v), _ptr(src_boxes), _ptr(tgt_boxes), _ptr(weight), _ptr(bias),
+                                                  _ptr(dim_t), float(scale), float(eps), _ptr(attn_mask), _ptr(out), _ptr(lse),
+                                                  _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gw), _ptr(gb), B, N, H, D,
+                                                  _ptr(ws), ws_bytes, _stream(q))
+    _lib.check(rc, "rdetr_relation_attention_backward")
+    return gq, gk, gv, gw, gb
+
+
+@relation_attention_backward.register_fake
+def _(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask, out, lse, grad_out):
+    H = q.shape[1]
+    return torch.empty_like(q), torch.empty_like(q), torch.empty_like(q), q.new_empty((H, 64)), q.new_empty((H,))
+
+
+def _relattn_setup_context(ctx, inputs, output):
+    q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, scale, eps, attn_mask = inputs
+    out, lse = output
+    ctx.save_for_backward(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, out, lse)
+    ctx.attn_mask = attn_mask
+    ctx.scale, ctx.eps = scale, eps
+    ctx.weight_shape = weight.shape
+
+
+def _relattn_autograd_backward(ctx, grad_out, grad_lse):
+    q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, out, lse = ctx.saved_tensors
+    gq, gk, gv, gw, gb = relation_attention_backward(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, ctx.scale, ctx.eps,
+                                                     ctx.attn_mask, out, lse, grad_out)
+    # no gradient reaches the boxes: the reference computes the geometry under no_grad (relation_transformer.py:527-529)
+    return gq, gk, gv, None, None, gw.view(ctx.weight_shape), gb, None, None, None, None
+
+
+relation_attention_forward.register_autograd(_relattn_autograd_backward, setup_context=_relattn_setup_context)
+
+
+def relation_attention(q: Tensor, k: Tensor, v: Tensor, src_boxes: Tensor, tgt_boxes: Tensor, weight: Tensor, bias: Tensor,
+                       dim_t: Optional[Tensor] = None, scale: float = 100.0, eps: float = 1e-5,
+                       attn_mask: Optional[Tensor] = None) -> Tensor:
+    """``softmax(q k^T / sqrt(D) + relu(W f(src, tgt) + c) [-inf where attn_mask]) v`` for ``q, k, v [B, H, N, D]`` without ever
+    materialising the ``[B, H, N, N]`` relation bias (reference: relation_transformer.py:369-374 + :453-459).  Differentiable
+    w.r.t. q, k, v, ``weight`` ([H,64] or [H,64,1,1]) and ``bias``."""
+    if dim_t is None:
+        dim_t = relation_dim_t(16, 10000.0, q.device)
+    out, _ = relation_attention_forward(q.float().contiguous(), k.float().contiguous(), v.float().contiguous(),
+                                        src_boxes.detach().float().contiguous(), tgt_boxes.detach().float().contiguous(),
+                                        weight.float().contiguous(), bias.float().contiguous(), dim_t, scale, eps, attn_mask)
     return out
 
 

@@ -36,13 +36,13 @@ def _fp32_matmuls():
     rinstall.uninstall()
 
 
-def _pair(build):
+def _pair(build, fused_attention=False):
     """(reference-built module, module built after install()) with identical weights."""
     refmodel.activate()
     rinstall.uninstall()
     torch.manual_seed(0)
     ref = build().to(DEV)
-    report = rinstall.install()
+    report = rinstall.install(fused_attention=fused_attention)
     assert not report.skipped and "models.bricks.relation_transformer.PositionRelationEmbedding" in report
     torch.manual_seed(0)
     ours = build().to(DEV)
@@ -96,15 +96,21 @@ def test_encoder_layer_matches_the_unmodified_reference():
         _assert_close(go_[n], gr[n], 2e-4, f"grad {n}")
 
 
-def test_decoder_matches_the_unmodified_reference():
+@pytest.mark.parametrize("fused_attention", [False, True])
+def test_decoder_matches_the_unmodified_reference(fused_attention):
+    """fused_attention=True additionally swaps the layers' nn.MultiheadAttention for RelationMultiheadAttention (row N1):
+    the relation bias of layers 1.. is generated inside the attention kernel instead of being materialised."""
     def build():
         from models.bricks import relation_transformer as rt
         layer = rt.RelationTransformerDecoderLayer(embed_dim=256, d_ffn=512, n_heads=8, dropout=0.0,
                                                    activation=torch.nn.ReLU(inplace=True), n_levels=4, n_points=4)
         return rt.RelationTransformerDecoder(decoder_layer=layer, num_layers=3, num_classes=91)
 
-    ref, ours = _pair(build)
+    ref, ours = _pair(build, fused_attention)
     assert isinstance(ours.position_relation_embedding, modules.PositionRelationEmbedding)
+    assert isinstance(ours.layers[0].self_attn, modules.RelationMultiheadAttention) == fused_attention
+    if fused_attention:
+        rinstall.install(fused_attention=True)  # the lazy hand-over is a class-level switch: keep it on while `ours` runs
     with torch.no_grad():
         for m in (ref, ours):
             torch.manual_seed(1)
@@ -137,7 +143,7 @@ def test_decoder_matches_the_unmodified_reference():
     gr, go_ = _grads(ref), _grads(ours)
     assert gr.keys() == go_.keys() and "position_relation_embedding.pos_proj.0.weight" in gr
     for n in gr:
-        _assert_close(go_[n], gr[n], 5e-4, f"grad {n}")
+        _assert_close(go_[n], gr[n], 3e-3 if "pos_proj" in n else 5e-4, f"grad {n}")
 
 
 def test_relation_detr_loss_dict_matches_the_unmodified_reference():
