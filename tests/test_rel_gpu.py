@@ -103,12 +103,13 @@ def test_relu_bits_mask_fusion_and_inplace_mutation():
                                                  100.0, 1e-5, mask, False)
     plain, bits2 = torch.ops.rdetr.relation_forward(r["src_boxes"], r["tgt_boxes"], r["weight"], r["bias"], dim_t,
                                                     100.0, 1e-5, None, False)
-    assert torch.equal(bits, bits2)
     assert torch.equal(out, plain.masked_fill(mask, float("-inf")))
-    # bits is [B, N1, words, H]; bit j%32 of word j/32 == (pre-activation > 0)
+    # bits is [B, N1, words, H]; bit j%32 of word j/32 == (pre-activation > 0), and 0 at blocked positions: the reference's
+    # masked_fill_ gives those elements no gradient whatever the caller sends back
     j = torch.arange(45, device=DEV)
-    unpacked = (bits[:, :, j // 32, :] >> (j % 32)[None, None, :, None]) & 1  # [B, N1, N2, H]
-    assert torch.equal(unpacked.bool().permute(0, 3, 1, 2), plain > 0)
+    unpack = lambda w: ((w[:, :, j // 32, :] >> (j % 32)[None, None, :, None]) & 1).bool().permute(0, 3, 1, 2)  # noqa: E731  [B, H, N1, N2]
+    assert torch.equal(unpack(bits2), plain > 0)
+    assert torch.equal(unpack(bits), (plain > 0) & ~mask[None, None])
 
 
 def test_equivariance_and_default_target():
