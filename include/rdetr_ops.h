@@ -207,6 +207,19 @@ int rdetr_relation_attention_backward(const float *q, const float *k, const floa
                                       rdetr_stream_t stream);
 
 /*
+ * The encoder's memory_fusion input Linear without the concatenation.
+ * Replaces torch.cat(queries, -1) -> Linear((L+1)*C, N) [-> ReLU] (upstream models/bricks/relation_transformer.py:168-173,
+ * 203-204): out = relu(sum_t sources[t] @ weight[:, t*C:(t+1)*C]^T + bias), the K loop walking the sources in place.
+ * Dense contraction => tcgen05.mma (kind::tf32, fp32 accumulation in TMEM), operands fetched by TMA.
+ *
+ *   sources  HOST array of nsrc DEVICE pointers, each [M, C] fp32 row-major, 16-byte aligned
+ *   weight   [N, nsrc*C] fp32 (nn.Linear layout)     bias [N] fp32     out [M, N] fp32
+ * Supported: N == 256, nsrc <= 8, C % 32 == 0.  TF32 products: use where the reference runs this GEMM in bf16 / tf32.
+ */
+int rdetr_memory_fusion_forward(const float *const *sources, int nsrc, const float *weight, const float *bias,
+                                float *out, long long M, int C, int N, int relu, rdetr_stream_t stream);
+
+/*
  * Batched rectangular linear-sum-assignment.
  * Replaces scipy.optimize.linear_sum_assignment(c.cpu()) at models/matcher/hungarian_matcher.py:80 and :87
  * (one device->host copy + host solve per image and per decoder layer).  All problems of one call are

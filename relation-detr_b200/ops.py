@@ -25,6 +25,7 @@ __all__ = [
     "msda_forward", "msda_backward", "ms_deform_attn", "MultiScaleDeformableAttnFunction",
     "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
     "relation_attention_forward", "relation_attention_backward", "relation_attention",
+    "memory_fusion_forward", "memory_fusion_linear",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
     "lsap_solve", "match_cost",
 ]
@@ -463,6 +464,67 @@ def relation_attention(q: Tensor, k: Tensor, v: Tensor, src_boxes: Tensor, tgt_b
                                         src_boxes.detach().float().contiguous(), tgt_boxes.detach().float().contiguous(),
                                         weight.float().contiguous(), bias.float().contiguous(), dim_t, scale, eps, attn_mask)
     return out
+
+
+# ---- memory_fusion input Linear without the concatenation --------------
+
+@torch.library.custom_op("rdetr::memory_fusion_forward", mutates_args=(), device_types="cuda")
+def memory_fusion_forward(sources: Sequence[Tensor], weight: Tensor, bias: Tensor, relu: bool) -> Tensor:
+    import ctypes
+
+    srcs = list(sources)
+    _require(len(srcs) > 0, "rdetr::memory_fusion: no source tensor")
+    C = srcs[0].shape[-1]
+    lead = srcs[0].shape[:-1]
+    flat = []
+    for t in srcs:
+        _require(t.is_cuda and t.dtype == torch.float32, "rdetr::memory_fusion: sources must be float32 CUDA tensors (no CPU path)")
+        _require(t.shape[-1] == C and t.shape[:-1] == lead, "rdetr::memory_fusion: sources must share one shape")
+        flat.append(t.reshape(-1, C).contiguous())
+    N = weight.shape[0]
+    _require(weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous() and weight.shape == (N, len(srcs) * C),
+             "rdetr::memory_fusion: weight must be a contiguous float32 [N, len(sources)*C] CUDA tensor")
+    _require(bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous() and bias.shape == (N,), "rdetr::memory_fusion: bias must be float32 [N]")
+    M = flat[0].shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=weight.device)
+    ptrs = (ctypes.c_void_p * len(flat))(*[t.data_ptr() for t in flat])
+    with torch.cuda.device(weight.device):
+        rc = _lib.lib().rdetr_memory_fusion_forward(ptrs, len(flat), _ptr(weight), _ptr(bias), _ptr(out), M, C, N, 1 if relu else 0,
+                                                    _stream(weight))
+    _lib.check(rc, "rdetr_memory_fusion_forward")
+    return out.view(*lead, N)
+
+
+@memory_fusion_forward.register_fake
+def _(sources, weight, bias, relu):
+    return sources[0].new_empty((*sources[0].shape[:-1], weight.shape[0]))
+
+
+def _memfuse_setup_context(ctx, inputs, output):
+    sources, weight, bias, relu = inputs
+    ctx.save_for_backward(weight, output, *sources)  # the sources themselves, not a concatenated copy
+    ctx.relu = relu
+
+
+def _memfuse_autograd_backward(ctx, grad_out):
+    weight, output, *sources = ctx.saved_tensors
+    C = sources[0].shape[-1]
+    g = grad_out.reshape(-1, weight.shape[0]).float()
+    if ctx.relu:
+        g = g * (output.reshape(-1, weight.shape[0]) > 0)
+    # plain library GEMMs on the original tensors: dX_t = g W_t, dW_t = g^T X_t
+    grads = [(g @ weight[:, t * C:(t + 1) * C]).view_as(x) for t, x in enumerate(sources)]
+    gw = torch.cat([g.t() @ x.reshape(-1, C) for x in sources], 1)
+    return grads, gw, g.sum(0), None
+
+
+memory_fusion_forward.register_autograd(_memfuse_autograd_backward, setup_context=_memfuse_setup_context)
+
+
+def memory_fusion_linear(sources: Sequence[Tensor], weight: Tensor, bias: Tensor, relu: bool = True) -> Tensor:
+    """``relu(torch.cat(sources, -1) @ weight.T + bias)`` without the concatenation: a K-split tcgen05 GEMM (TF32 products, fp32
+    accumulation) whose A operand walks ``sources`` in place (reference: relation_transformer.py:168-173, 203-204)."""
+    return memory_fusion_forward([s.float() for s in sources], weight.float().contiguous(), bias.float().contiguous(), relu)
 
 
 # ---- batched linear-sum-assignment (SURVEY.md section 8, row N3) -------------------------------------
