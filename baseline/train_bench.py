@@ -6,6 +6,8 @@ is the reference's (``baseline/train_step.py``).  Three operator paths:
   ours            ``relation_detr_b200.install.install()`` before the model is built: B200 MSDA / relation / matcher
   ours_fused_attention  the same plus ``install(fused_attention=True)``: the decoder's self-attention generates the relation
                   bias inside the attention kernel
+  ours_all        everything: also ``install(fused_memory=True)`` (memory_fusion's input Linear as the K-split tcgen05 GEMM, row N4;
+                  active under autocast / allow_tf32)
   reference       the unmodified reference as it runs on this image (its extension does not build -> grid_sample path,
                   eager relation embedding, SciPy matcher with one device->host copy per prediction set)
   reference_cuda  the unmodified reference with its own CUDA kernel (``oracle/_ref``, sources untouched, sm_100a)
@@ -49,8 +51,8 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     rank = dist.get_rank() if world > 1 else 0
     refmodel.activate()
     rinstall.uninstall()
-    if path in ("ours", "ours_fused_attention"):
-        report = rinstall.install(fused_attention=(path == "ours_fused_attention"))
+    if path in ("ours", "ours_fused_attention", "ours_all"):
+        report = rinstall.install(fused_attention=(path in ("ours_fused_attention", "ours_all")), fused_memory=(path == "ours_all"))
         assert not report.skipped
         ext = "rdetr"
     else:
@@ -59,7 +61,7 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
             return {"unavailable": "oracle/_ref (the reference's own CUDA kernel, prebuilt) is not present"}
     torch.manual_seed(0)
     model, _ = refmodel.build_relation_detr_r50(enc_layers=enc_layers, dec_layers=dec_layers)
-    if path != "ours_fused_attention":  # the lazy relation-bias hand-over is a class-level switch: it stays on while the model runs
+    if path not in ("ours_fused_attention", "ours_all"):  # the lazy relation-bias hand-over is a class-level switch: it stays on while the model runs
         rinstall.uninstall()
     model = model.to(dev).train()
     n_params = sum(p.numel() for p in model.parameters())

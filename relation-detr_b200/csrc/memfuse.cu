@@ -22,6 +22,7 @@
 // a protocol error traps instead of hanging the device.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,7 +33,6 @@ constexpr int kMfBM = 128;        // rows per CTA
 constexpr int kMfBN = 256;        // output features (the whole width)
 constexpr int kMfBK = 32;         // floats per stage along K = one 128-byte swizzle row
 constexpr int kMfUmmaK = 8;       // tf32: 32 bytes per MMA along K
-constexpr int kMfStages = 4;
 constexpr int kMfMaxSrc = 8;
 constexpr int kMfThreads = 192;
 constexpr uint32_t kMfBytesA = kMfBM * kMfBK * 4;  // 16 KB
@@ -86,7 +86,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256 (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
 constexpr uint32_t kMfIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kMfBN >> 3) << 17) | ((uint32_t)(kMfBM >> 4) << 24);
 
-__global__ void __launch_bounds__(kMfThreads, 1)
+// STAGES = 4: one CTA per SM (193 KB of shared memory); STAGES = 2: two CTAs per SM (97 KB each, 2 x 256 TMEM columns), so
+// that one CTA's epilogue overlaps the other's main loop.
+template <int kMfStages>
+__global__ void __launch_bounds__(kMfThreads, kMfStages <= 2 ? 2 : 1)
 memfuse_kernel(const __grid_constant__ MfMaps maps, const float *__restrict__ bias, float *__restrict__ out, int M, int nsrc,
                int kb_per_src, int src_cols, int relu)
 {
@@ -244,11 +247,16 @@ extern "C" int rdetr_memory_fusion_forward(const float *const *sources, int nsrc
     for (int t = 0; t < nsrc; ++t)
         if (int rc = make_map(&maps.a[t], sources[t], (uint64_t)M, (uint64_t)C, (uint64_t)C, kMfBM)) return rc;
     if (int rc = make_map(&maps.w, weight, (uint64_t)N, (uint64_t)nsrc * C, (uint64_t)nsrc * C, kMfBN)) return rc;
-    const size_t smem = (size_t)kMfStages * kMfStageBytes + 1024;
-    if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                            "cudaFuncSetAttribute(memfuse)"))
-        return rc;
+    static const int stages = [] { const char *e = getenv("RDETR_MEMFUSE_STAGES"); const int v = e ? atoi(e) : 0; return v == 4 ? 4 : 2; }();
     const unsigned grid = (unsigned)((M + kMfBM - 1) / kMfBM);
-    memfuse_kernel<<<grid, kMfThreads, smem, static_cast<cudaStream_t>(stream)>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t)stages * kMfStageBytes + 1024;
+    if (stages == 4) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(memfuse)")) return rc;
+        memfuse_kernel<4><<<grid, kMfThreads, smem, st>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu);
+    } else {
+        if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(memfuse)")) return rc;
+        memfuse_kernel<2><<<grid, kMfThreads, smem, st>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu);
+    }
     return check_cuda(cudaGetLastError(), "memfuse_kernel launch");
 }

@@ -57,13 +57,15 @@ class _NNProxy:
 
 
 def install(reference_root: str | None = None, strict: bool = True, matcher_too: bool = True,
-            fused_attention: bool = False) -> InstallReport:
+            fused_attention: bool = False, fused_memory: bool = False) -> InstallReport:
     """Returns the ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
     ``HungarianMatcher`` (device-resident matching): its index tensors are CUDA
     tensors, which every use in ``models/bricks/set_criterion.py`` accepts.  ``fused_attention`` (row N1) makes the
     relation decoder's self-attention generate the position-relation bias inside the attention kernel:
     ``PositionRelationEmbedding`` hands out a lazy handle and the decoder layer's ``nn.MultiheadAttention`` becomes
-    ``RelationMultiheadAttention`` (same parameters, same state-dict keys)."""
+    ``RelationMultiheadAttention`` (same parameters, same state-dict keys).  ``fused_memory`` (row N4) replaces
+    ``RelationTransformerEncoder`` by a subclass whose ``memory_fusion`` input Linear reads the encoder states in place
+    (tcgen05 GEMM) instead of concatenating them."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     report = InstallReport()
@@ -108,6 +110,13 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
         if "PositionRelationEmbedding.lazy" not in _saved:
             _saved["PositionRelationEmbedding.lazy"] = modules.PositionRelationEmbedding.lazy
         modules.PositionRelationEmbedding.lazy = True
+    if fused_memory:
+        try:
+            mod = importlib.import_module("models.bricks.relation_transformer")
+        except Exception as e:
+            raise RuntimeError(f"relation_detr_b200.install: cannot import models.bricks.relation_transformer ({type(e).__name__}: {e})") from e
+        base = _saved.get("models.bricks.relation_transformer.RelationTransformerEncoder", mod.RelationTransformerEncoder)
+        rebind(mod, "models.bricks.relation_transformer", "RelationTransformerEncoder", modules.make_fused_encoder(base))
     if strict and not report:
         raise RuntimeError("relation_detr_b200.install: no name of the reference was rebound")
     return report

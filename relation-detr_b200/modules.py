@@ -247,3 +247,32 @@ class RelationMultiheadAttention(nn.MultiheadAttention):
                                       emb._dim_t_on(query.device), emb.scale, emb.eps, rel.mask)
         core = core.transpose(1, 2).reshape(B, N, E).to(q.dtype)
         return self.out_proj(core), None
+
+
+def make_fused_encoder(base):
+    """``RelationTransformerEncoder`` (upstream ``relation_transformer.py:153-205``) whose last step does not concatenate the
+    layer outputs: ``memory_fusion``'s input Linear walks the ``num_layers + 1`` states in place on the tensor cores
+    (``rdetr::memory_fusion_forward``, SURVEY.md section 8 row N4).  Same parameters, same state-dict keys; built by
+    ``install(fused_memory=True)`` as a subclass of the reference's own class so that the layer loop stays upstream's.
+
+    The kernel multiplies in TF32.  It is used where upstream runs this GEMM at reduced precision anyway -- under autocast
+    (bf16 there) or with ``torch.backends.cuda.matmul.allow_tf32`` -- and strict-fp32 calls keep upstream's expression."""
+
+    class RelationTransformerEncoder(base):
+        def forward(self, query, spatial_shapes, level_start_index, reference_points, query_pos=None, query_key_padding_mask=None):
+            queries = [query]
+            for layer in self.layers:
+                query = layer(query, query_pos, reference_points, spatial_shapes, level_start_index, query_key_padding_mask)
+                queries.append(query)
+            lin1, act, lin2, norm = self.memory_fusion
+            reduced = torch.is_autocast_enabled() or torch.backends.cuda.matmul.allow_tf32
+            if (reduced and query.is_cuda and isinstance(act, nn.ReLU) and lin1.out_features == 256 and len(queries) <= 8
+                    and query.shape[-1] % 32 == 0 and lin1.bias is not None):
+                hidden = ops.memory_fusion_linear(queries, lin1.weight, lin1.bias, True)
+            else:
+                hidden = act(lin1(torch.cat(queries, -1)))
+            return norm(lin2(hidden))
+
+    RelationTransformerEncoder.__qualname__ = "RelationTransformerEncoder"
+    RelationTransformerEncoder.__module__ = base.__module__
+    return RelationTransformerEncoder

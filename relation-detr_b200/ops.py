@@ -504,18 +504,31 @@ def _memfuse_setup_context(ctx, inputs, output):
     sources, weight, bias, relu = inputs
     ctx.save_for_backward(weight, output, *sources)  # the sources themselves, not a concatenated copy
     ctx.relu = relu
+    ctx.autocast = torch.is_autocast_enabled()
 
 
 def _memfuse_autograd_backward(ctx, grad_out):
+    """Plain library GEMMs on the original tensors: dX_t = g W_t, dW_t = g^T X_t, at the precision the forward ran the contraction
+    in -- bf16 when the forward was called under autocast (what upstream's autocast backward does), TF32 otherwise."""
     weight, output, *sources = ctx.saved_tensors
-    C = sources[0].shape[-1]
-    g = grad_out.reshape(-1, weight.shape[0]).float()
+    C, N = sources[0].shape[-1], weight.shape[0]
+    g = grad_out.reshape(-1, N).float()
     if ctx.relu:
-        g = g * (output.reshape(-1, weight.shape[0]) > 0)
-    # plain library GEMMs on the original tensors: dX_t = g W_t, dW_t = g^T X_t
-    grads = [(g @ weight[:, t * C:(t + 1) * C]).view_as(x) for t, x in enumerate(sources)]
-    gw = torch.cat([g.t() @ x.reshape(-1, C) for x in sources], 1)
-    return grads, gw, g.sum(0), None
+        g = g * (output.reshape(-1, N) > 0)
+    gb = g.sum(0)
+    if ctx.autocast:
+        g16, w16 = g.bfloat16(), weight.bfloat16()
+        grads = [(g16 @ w16[:, t * C:(t + 1) * C]).float().view_as(x) for t, x in enumerate(sources)]
+        gw = torch.cat([(g16.t() @ x.reshape(-1, C).bfloat16()).float() for x in sources], 1)
+        return grads, gw, gb, None
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        grads = [(g @ weight[:, t * C:(t + 1) * C]).view_as(x) for t, x in enumerate(sources)]
+        gw = torch.cat([g.t() @ x.reshape(-1, C) for x in sources], 1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return grads, gw, gb, None
 
 
 memory_fusion_forward.register_autograd(_memfuse_autograd_backward, setup_context=_memfuse_setup_context)

@@ -36,13 +36,13 @@ def _fp32_matmuls():
     rinstall.uninstall()
 
 
-def _pair(build, fused_attention=False):
+def _pair(build, fused_attention=False, fused_memory=False):
     """(reference-built module, module built after install()) with identical weights."""
     refmodel.activate()
     rinstall.uninstall()
     torch.manual_seed(0)
     ref = build().to(DEV)
-    report = rinstall.install(fused_attention=fused_attention)
+    report = rinstall.install(fused_attention=fused_attention, fused_memory=fused_memory)
     assert not report.skipped and "models.bricks.relation_transformer.PositionRelationEmbedding" in report
     torch.manual_seed(0)
     ours = build().to(DEV)
@@ -94,6 +94,44 @@ def test_encoder_layer_matches_the_unmodified_reference():
     assert gr.keys() == go_.keys()
     for n in gr:
         _assert_close(go_[n], gr[n], 2e-4, f"grad {n}")
+
+
+def test_encoder_with_fused_memory_fusion_matches_the_unmodified_reference():
+    """install(fused_memory=True): RelationTransformerEncoder's memory_fusion input Linear runs as the K-split tcgen05 GEMM
+    (TF32) whenever the GEMM may run at reduced precision; compared with the unmodified encoder under allow_tf32 (the
+    reference then runs its cat -> Linear in TF32 too), and bit-for-bit policy-checked in strict fp32."""
+    def build():
+        from models.bricks import relation_transformer as rt
+        layer = rt.RelationTransformerEncoderLayer(embed_dim=256, d_ffn=512, dropout=0.0, n_heads=8,
+                                                   activation=torch.nn.ReLU(inplace=True), n_levels=4, n_points=4)
+        return rt.RelationTransformerEncoder(layer, num_layers=3)
+
+    ref, ours = _pair(build, fused_memory=True)
+    assert type(ours).__name__ == "RelationTransformerEncoder" and type(ours) is not type(ref) and isinstance(ours, type(ref))
+    ss, lsi = workloads.shape_tensors(LEVELS, DEV)
+    S = int(ss.prod(1).sum())
+    g = torch.Generator(device=DEV).manual_seed(7)
+    query = torch.randn((2, S, 256), device=DEV, generator=g)
+    pos = torch.randn((2, S, 256), device=DEV, generator=g) * 0.1
+    refp = workloads.full_reference_points(LEVELS, DEV)[None, :, None, :].expand(2, S, 4, 2).contiguous()
+    go = torch.randn((2, S, 256), device=DEV, generator=g)
+
+    def run(m):
+        m.zero_grad()
+        out = m(query, ss, lsi, refp, query_pos=pos, query_key_padding_mask=None)
+        out.backward(go)
+        return out.detach(), _grads(m)
+
+    # strict fp32: the subclass keeps upstream's expression -> same numbers as the first integration test's tolerance
+    o_ref, g_ref = run(ref)
+    o_our, g_our = run(ours)
+    _assert_close(o_our, o_ref, 2e-5, "encoder output (fp32 policy)")
+    torch.backends.cuda.matmul.allow_tf32 = True  # the fixture restores it
+    o_ref, g_ref = run(ref)
+    o_our, g_our = run(ours)
+    _assert_close(o_our, o_ref, 5e-3, "encoder output (tf32 policy: kernel vs cuBLAS TF32)")
+    for n in g_ref:
+        _assert_close(g_our[n], g_ref[n], 2e-2, f"grad {n}")
 
 
 @pytest.mark.parametrize("fused_attention", [False, True])
