@@ -455,6 +455,112 @@ def gpu_side_baselines(torch, ops, wl, inp, steps):
     return out
 
 
+def time_relation_attention(torch, ops, wl, B, N, dn, steps, warmup):
+    """Row N1: decoder self-attention with the relation bias generated inside the kernel vs the chain it replaces (our fused
+    relation-bias kernel -> SDPA with the materialised float mask; `as_reference` adds upstream's separate masked_fill_)."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    q, k, v = (torch.randn((B, 8, N, 32), device=dev, generator=g).requires_grad_(True) for _ in range(3))
+    src, tgt = wl.make_boxes(B, N, 1, dev), wl.make_boxes(B, N, 2, dev)
+    w, b = wl.make_rel_params(8, 64, 0, dev)
+    w.requires_grad_(True)
+    b.requires_grad_(True)
+    mask = wl.cdn_attn_mask(N - dn, 10, dn // 10, dev) if dn else None
+    go = torch.randn((B, 8, N, 32), device=dev, generator=g)
+
+    def fused():
+        return ops.relation_attention(q, k, v, src, tgt, w, b, attn_mask=mask)
+
+    def unfused():
+        bias = ops.position_relation_bias(src, tgt, w, b, attn_mask=mask, fast=True)
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias)
+
+    def as_reference():
+        bias = ops.position_relation_bias(src, tgt, w, b, fast=True).flatten(0, 1)
+        if mask is not None:
+            bias.masked_fill_(mask, float("-inf"))
+        return torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=bias.view(B, 8, N, N))
+
+    def timed(fn, n):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def fb(f):
+        def run():
+            for t in (q, k, v, w, b):
+                t.grad = None
+            f().backward(go)
+        return run
+
+    out = {"B": B, "N": N, "masked": bool(dn)}
+    for name, f in (("fused", fused), ("unfused", unfused), ("unfused_as_reference", as_reference)):
+        torch.cuda.reset_peak_memory_stats()
+        out[name] = {"fwd_ms": round(timed(f, steps), 4), "fwd_bwd_ms": round(timed(fb(f), steps), 4),
+                     "peak_mem_MB": round(torch.cuda.max_memory_allocated() / 2**20, 1)}
+    return out
+
+
+def time_memory_fusion(torch, ops, B, S, steps, warmup, peak_hbm):
+    """Row N4: memory_fusion's input Linear as the K-split tcgen05 GEMM over the 7 encoder states in place vs upstream's
+    torch.cat -> Linear -> ReLU (fp32, TF32 and bf16-autocast library GEMMs).  Roofline: HBM (the GEMM moves 1.46 GB for
+    164 GFLOP: 112 FLOP/B, below the TF32 ridge) and the tensor pipe against the measured bf16 peak / 2 (TF32 = half rate)."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    srcs = [torch.randn((B, S, 256), device=dev, generator=g) for _ in range(7)]
+    lin = torch.nn.Linear(1792, 256).to(dev)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def ref_bf16():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return torch.relu(lin(torch.cat(srcs, -1)))
+
+    def ref_tf32():
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return torch.relu(lin(torch.cat(srcs, -1)))
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+
+    with torch.no_grad():
+        t_ours = timed(lambda: ops.memory_fusion_linear(srcs, lin.weight, lin.bias, True))
+        t_fp32 = timed(lambda: torch.relu(lin(torch.cat(srcs, -1))))
+        t_tf32 = timed(ref_tf32)
+        t_bf16 = timed(ref_bf16)
+    M = B * S
+    flops, nbytes = 2.0 * M * 1792 * 256, (7 * M * 256 + M * 256 + 1792 * 256 + 256) * 4
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            bf16_peak = float(json.load(f)["bf16_tflops"])
+    except Exception:
+        bf16_peak = 1590.0
+    return {"workload": f"memory_fusion input Linear, 7 x [{B}, {S}, 256] -> 256, fp32 in / out", "kernel": "memfuse_kernel (tcgen05.mma kind::tf32, TMA, TMEM)",
+            "fwd_ms": round(t_ours, 4), "torch_cat_linear_fp32_ms": round(t_fp32, 4), "torch_cat_linear_tf32_ms": round(t_tf32, 4),
+            "torch_cat_linear_bf16_autocast_ms": round(t_bf16, 4),
+            "roofline": {"bound": "hbm", "achieved": round(nbytes / t_ours / 1e6, 1), "peak": peak_hbm, "unit": "GB/s",
+                         "frac": round(nbytes / t_ours / 1e6 / peak_hbm, 4), "algorithmic_bytes": nbytes,
+                         "tensor": {"achieved": round(flops / t_ours / 1e9, 1), "peak": round(bf16_peak / 2, 1), "unit": "TFLOP/s (TF32 = half the measured bf16 burst peak)",
+                                    "frac": round(flops / t_ours / 1e9 / (bf16_peak / 2), 4)}}}
+
+
 def run_train_block(args, world, rank, quick: bool):
     """BASELINE configs[3] on the real model (baseline/train_bench.py).  Every rank takes part (DDP); rank 0 keeps the result."""
     from baseline import refmodel, train_bench
@@ -572,6 +678,9 @@ def run_ours(args):
             guarded(name + "_fast", lambda name=name: time_rel(torch, ops, workloads, name, k, w, True))
         guarded("matching_step_b2", lambda: time_matching(torch, rd, k, w))
         guarded("gpu_baselines", lambda: gpu_side_baselines(torch, ops, workloads, inp, k))
+        guarded("relation_attention_b8_n900", lambda: time_relation_attention(torch, ops, workloads, 8, 900, 0, k, w))
+        guarded("relation_attention_b8_n1100_masked", lambda: time_relation_attention(torch, ops, workloads, 8, 1100, 200, k, w))
+        guarded("memory_fusion_b8", lambda: time_memory_fusion(torch, ops, 8, shape.S, k, w, peak))
     if rank == 0 and not args.no_cpu_baseline:
         # the same sample as one step of `--impl reference` (a full batch-8 pass), 1 warm-up + 3 timed: ~10 s of host work
         gbs, cms, cores, sample = time_cpu_port(3, 1, shape.batch, args.loc)
@@ -618,6 +727,7 @@ def run_ours(args):
                          "algorithmic_bytes": bwd_b, "peak_source": peak_src,
                          "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
                          "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4), "rel": rel_roof,
+                         "memory_fusion": (extra.get("memory_fusion_b8") or {}).get("roofline") if isinstance(extra.get("memory_fusion_b8"), dict) else None,
                          # the resources that actually bind: one 128-byte row per bilinear corner
                          "binding": {
                              "corner_rows_per_launch": corner_rows,
