@@ -7,7 +7,8 @@ is the reference's (``baseline/train_step.py``).  Three operator paths:
   ours_fused_attention  the same plus ``install(fused_attention=True)``: the decoder's self-attention generates the relation
                   bias inside the attention kernel
   ours_all        everything: also ``install(fused_memory=True)`` (memory_fusion's input Linear as the K-split tcgen05 GEMM, row N4;
-                  active under autocast / allow_tf32)
+                  active under autocast / allow_tf32) and ``install(fused_topk=True)`` (the two-stage selection's torch.topk as
+                  rdetr_topk_rows)
   reference       the unmodified reference as it runs on this image (its extension does not build -> grid_sample path,
                   eager relation embedding, SciPy matcher with one device->host copy per prediction set)
   reference_cuda  the unmodified reference with its own CUDA kernel (``oracle/_ref``, sources untouched, sm_100a)
@@ -52,7 +53,8 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     refmodel.activate()
     rinstall.uninstall()
     if path in ("ours", "ours_fused_attention", "ours_all"):
-        report = rinstall.install(fused_attention=(path in ("ours_fused_attention", "ours_all")), fused_memory=(path == "ours_all"))
+        report = rinstall.install(fused_attention=(path in ("ours_fused_attention", "ours_all")), fused_memory=(path == "ours_all"),
+                                  fused_topk=(path == "ours_all"))
         assert not report.skipped
         ext = "rdetr"
     else:

@@ -561,6 +561,46 @@ def time_memory_fusion(torch, ops, B, S, steps, warmup, peak_hbm):
                                     "frac": round(flops / t_ours / 1e9 / (bf16_peak / 2), 4)}}}
 
 
+def time_two_stage(torch, ops, B, S, K, steps, warmup, peak_hbm, C=91):
+    """Row N4, second half: the two-stage query selection (row maxima -> cluster radix select -> row gather, 3 launches) vs
+    upstream's expression (relation_transformer.py:90-96: sigmoid over all boxes, max, torch.topk, two gathers).  Index work:
+    HBM bound on the one read of the class logits [B, S, C]."""
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    cls = torch.randn((B, S, C), device=dev, generator=g) - 4.6
+    box = torch.randn((B, S, 4), device=dev, generator=g)
+    scores = cls.max(-1)[0]
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps * 3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (steps * 3)
+
+    def upstream():
+        coord = box.sigmoid()
+        idx = torch.topk(cls.max(-1)[0], K, dim=1)[1].unsqueeze(-1)
+        return cls.gather(1, idx.expand(-1, -1, C)), coord.gather(1, idx.expand(-1, -1, 4))
+
+    with torch.no_grad():
+        t_ours = timed(lambda: ops.two_stage_select(cls, box, K))
+        t_ref = timed(upstream)
+        t_topk = timed(lambda: ops.topk_rows(scores, K))
+        t_torch_topk = timed(lambda: torch.topk(scores, K, dim=1))
+    nbytes = (B * S * C + B * K * (C + 4 + 4 + 2)) * 4
+    return {"workload": f"two-stage selection, class logits [{B}, {S}, {C}] fp32, k = {K}", "kernels": "rowmax_kernel, topk_select_kernel (8-CTA cluster per image, DSMEM histograms), gather_rows_kernel",
+            "fwd_ms": round(t_ours, 4), "upstream_expression_ms": round(t_ref, 4), "topk_rows_ms": round(t_topk, 4), "torch_topk_ms": round(t_torch_topk, 4),
+            "note": "times include the torch dispatch of each call (3 launches ours, 7 upstream)",
+            "roofline": {"bound": "hbm", "achieved": round(nbytes / t_ours / 1e6, 1), "peak": peak_hbm, "unit": "GB/s",
+                         "frac": round(nbytes / t_ours / 1e6 / peak_hbm, 4), "algorithmic_bytes": nbytes}}
+
+
 def run_train_block(args, world, rank, quick: bool):
     """BASELINE configs[3] on the real model (baseline/train_bench.py).  Every rank takes part (DDP); rank 0 keeps the result."""
     from baseline import refmodel, train_bench
@@ -681,6 +721,8 @@ def run_ours(args):
         guarded("relation_attention_b8_n900", lambda: time_relation_attention(torch, ops, workloads, 8, 900, 0, k, w))
         guarded("relation_attention_b8_n1100_masked", lambda: time_relation_attention(torch, ops, workloads, 8, 1100, 200, k, w))
         guarded("memory_fusion_b8", lambda: time_memory_fusion(torch, ops, 8, shape.S, k, w, peak))
+        guarded("two_stage_select_b8", lambda: time_two_stage(torch, ops, 8, shape.S, 900, k, w, peak))
+        guarded("two_stage_select_1200x2000_b1", lambda: time_two_stage(torch, ops, 1, workloads.MSDA_SHAPES["msda_enc_1200x2000_b1"].S, 900, k, w, peak))
     if rank == 0 and not args.no_cpu_baseline:
         # the same sample as one step of `--impl reference` (a full batch-8 pass), 1 warm-up + 3 timed: ~10 s of host work
         gbs, cms, cores, sample = time_cpu_port(3, 1, shape.batch, args.loc)

@@ -220,6 +220,33 @@ int rdetr_memory_fusion_forward(const float *const *sources, int nsrc, const flo
                                 float *out, long long M, int C, int N, int relu, rdetr_stream_t stream);
 
 /*
+ * Two-stage query selection (second half).  Replaces, in RelationTransformer.forward
+ * (upstream models/bricks/relation_transformer.py:90-96 and :104-111),
+ *   enc_outputs_coord = (bbox_head(output_memory) + output_proposals).sigmoid()
+ *   topk_index = torch.topk(enc_outputs_class.max(-1)[0], topk, dim=1)[1]
+ *   enc_outputs_class.gather(1, topk_index...) ; enc_outputs_coord.gather(1, topk_index...)
+ * by three launches: row maxima, one-CTA-per-image radix select + sort, row gather (sigmoid applied to the K selected
+ * boxes only).  Index work: topk_index is torch.topk's (scores descending, NaN first); EQUAL scores are returned in
+ * ascending index order, a deterministic refinement of torch's unspecified tie order.
+ *
+ *   class_logits [B, S, C] fp32     coord [B, S, 4] fp32 or NULL (then topk_coord must be NULL)
+ *   apply_sigmoid  non-zero: coord holds pre-sigmoid boxes, topk_coord = sigmoid(selected rows), torch's arithmetic
+ *   topk_class [B, K, C], topk_coord [B, K, 4], topk_index [B, K] int64; K <= S, K <= 4096
+ *   workspace  rdetr_two_stage_workspace_bytes(B, S) bytes (the row maxima)
+ * rdetr_topk_rows is the middle launch alone: torch.topk(scores, K, dim=1) for scores [B, S] (values may be NULL).
+ * Backward: grad_class [B, S, C] / grad_coord [B, S, 4] are ZEROED INSIDE the call, then the K selected rows are
+ * written (with sigmoid' = (1 - y) * y from topk_coord when apply_sigmoid); either gradient may be NULL.
+ */
+size_t rdetr_two_stage_workspace_bytes(int B, int S);
+int rdetr_topk_rows(const float *scores, int B, int S, int K, int64_t *indices, float *values, rdetr_stream_t stream);
+int rdetr_two_stage_select(const float *class_logits, const float *coord, int B, int S, int C, int K, int apply_sigmoid,
+                           float *topk_class, float *topk_coord, int64_t *topk_index, void *workspace,
+                           size_t workspace_bytes, rdetr_stream_t stream);
+int rdetr_two_stage_select_backward(const float *grad_topk_class, const float *grad_topk_coord, const float *topk_coord,
+                                    const int64_t *topk_index, int B, int S, int C, int K, int apply_sigmoid,
+                                    float *grad_class, float *grad_coord, rdetr_stream_t stream);
+
+/*
  * Batched rectangular linear-sum-assignment.
  * Replaces scipy.optimize.linear_sum_assignment(c.cpu()) at models/matcher/hungarian_matcher.py:80 and :87
  * (one device->host copy + host solve per image and per decoder layer).  All problems of one call are

@@ -34,6 +34,10 @@ _SIGNATURES = {
     "rdetr_relation_attention_forward": (c_int, [c_void_p] * 8 + [c_float, c_float] + [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_relation_attention_backward": (c_int, [c_void_p] * 8 + [c_float, c_float] + [c_void_p] * 9 + [c_int] * 4 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_memory_fusion_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
+    "rdetr_two_stage_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "rdetr_topk_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rdetr_two_stage_select": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] * 4 + [c_size_t, c_void_p]),
+    "rdetr_two_stage_select_backward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 3),
     "rdetr_lsap_workspace_bytes": (c_size_t, [c_void_p, c_void_p, c_int]),
     "rdetr_lsap_solve": (c_int, [c_void_p] * 6 + [c_int, c_void_p, c_size_t, c_void_p]),
     "rdetr_match_cost": (c_int, [c_void_p] * 7 + [c_int, c_float, c_float, c_float, c_double, c_double, c_int, c_void_p]),

@@ -56,8 +56,30 @@ class _NNProxy:
         return getattr(torch.nn, name)
 
 
+class _TorchProxy:
+    """Stands in for the name ``torch`` inside ``models.bricks.relation_transformer``: every attribute is ``torch``'s except
+    ``topk``, so that the two-stage selection of ``RelationTransformer.forward`` (``relation_transformer.py:94, :109``:
+    ``torch.topk(enc_outputs_class.max(-1)[0], topk, dim=1)``) runs as one CTA per image (``rdetr_topk_rows``) without the
+    file being edited.  Calls the kernel does not cover (other ranks, dims, dtypes, k > 4096, CPU tensors) are torch's own."""
+
+    def __getattr__(self, name):
+        import torch
+
+        return getattr(torch, name)
+
+    @staticmethod
+    def topk(input, k, dim=-1, largest=True, sorted=True, **kwargs):
+        import torch
+
+        if (isinstance(input, torch.Tensor) and input.is_cuda and input.dim() == 2 and dim in (1, -1) and largest and sorted
+                and not kwargs and input.dtype in (torch.float32, torch.bfloat16, torch.float16) and 0 < int(k) <= min(4096, input.shape[1])):
+            values, indices = ops.topk_rows(input.float(), int(k))   # widening is exact: same order
+            return torch.return_types.topk((input.gather(1, indices) if input.dtype != torch.float32 else values, indices))
+        return torch.topk(input, k, dim=dim, largest=largest, sorted=sorted, **kwargs)
+
+
 def install(reference_root: str | None = None, strict: bool = True, matcher_too: bool = True,
-            fused_attention: bool = False, fused_memory: bool = False) -> InstallReport:
+            fused_attention: bool = False, fused_memory: bool = False, fused_topk: bool = False) -> InstallReport:
     """Returns the ``module.attribute`` names that were rebound.  ``matcher_too`` also replaces
     ``HungarianMatcher`` (device-resident matching): its index tensors are CUDA
     tensors, which every use in ``models/bricks/set_criterion.py`` accepts.  ``fused_attention`` (row N1) makes the
@@ -65,7 +87,8 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
     ``PositionRelationEmbedding`` hands out a lazy handle and the decoder layer's ``nn.MultiheadAttention`` becomes
     ``RelationMultiheadAttention`` (same parameters, same state-dict keys).  ``fused_memory`` (row N4) replaces
     ``RelationTransformerEncoder`` by a subclass whose ``memory_fusion`` input Linear reads the encoder states in place
-    (tcgen05 GEMM) instead of concatenating them."""
+    (tcgen05 GEMM) instead of concatenating them.  ``fused_topk`` (row N4, second half) routes the two ``torch.topk`` calls of
+    ``RelationTransformer.forward`` to ``rdetr_topk_rows`` (same indices; equal scores in ascending index order)."""
     if reference_root and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     report = InstallReport()
@@ -117,6 +140,12 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
             raise RuntimeError(f"relation_detr_b200.install: cannot import models.bricks.relation_transformer ({type(e).__name__}: {e})") from e
         base = _saved.get("models.bricks.relation_transformer.RelationTransformerEncoder", mod.RelationTransformerEncoder)
         rebind(mod, "models.bricks.relation_transformer", "RelationTransformerEncoder", modules.make_fused_encoder(base))
+    if fused_topk:
+        try:
+            mod = importlib.import_module("models.bricks.relation_transformer")
+        except Exception as e:
+            raise RuntimeError(f"relation_detr_b200.install: cannot import models.bricks.relation_transformer ({type(e).__name__}: {e})") from e
+        rebind(mod, "models.bricks.relation_transformer", "torch", _TorchProxy())
     if strict and not report:
         raise RuntimeError("relation_detr_b200.install: no name of the reference was rebound")
     return report

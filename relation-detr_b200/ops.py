@@ -26,6 +26,7 @@ __all__ = [
     "msda_fused_forward", "msda_fused_backward", "ms_deform_attn_fused",
     "relation_attention_forward", "relation_attention_backward", "relation_attention",
     "memory_fusion_forward", "memory_fusion_linear",
+    "topk_rows", "two_stage_select_forward", "two_stage_select_backward", "two_stage_select",
     "relation_forward", "relation_backward", "position_relation_bias", "relation_dim_t",
     "lsap_solve", "match_cost",
 ]
@@ -538,6 +539,95 @@ def memory_fusion_linear(sources: Sequence[Tensor], weight: Tensor, bias: Tensor
     """``relu(torch.cat(sources, -1) @ weight.T + bias)`` without the concatenation: a K-split tcgen05 GEMM (TF32 products, fp32
     accumulation) whose A operand walks ``sources`` in place (reference: relation_transformer.py:168-173, 203-204)."""
     return memory_fusion_forward([s.float() for s in sources], weight.float().contiguous(), bias.float().contiguous(), relu)
+
+
+# ---- two-stage query selection (SURVEY.md section 8, row N4, second half) ---------------------------
+
+def topk_rows(scores: Tensor, k: int) -> Tuple[Tensor, Tensor]:
+    """``torch.topk(scores, k, dim=1)`` for float32 ``scores [B, S]`` on the GPU: one CTA per row (radix select + sort in
+    shared memory).  Same values and indices as torch; equal scores come out in ascending index order.  The values are
+    gathered with torch so that they stay differentiable, as ``torch.topk``'s are."""
+    _require(scores.is_cuda and scores.dtype == torch.float32 and scores.dim() == 2,
+             "rdetr::topk_rows: scores must be a float32 [B, S] CUDA tensor (no CPU path)")
+    s = scores.detach().contiguous()
+    B, S = s.shape
+    idx = torch.empty((B, k), dtype=torch.int64, device=s.device)
+    with torch.cuda.device(s.device):
+        rc = _lib.lib().rdetr_topk_rows(_ptr(s), B, S, int(k), _ptr(idx), 0, _stream(s))
+    _lib.check(rc, "rdetr_topk_rows")
+    return scores.gather(1, idx), idx
+
+
+@torch.library.custom_op("rdetr::two_stage_select_forward", mutates_args=(), device_types="cuda")
+def two_stage_select_forward(class_logits: Tensor, coord: Tensor, k: int, sigmoid: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    _require(class_logits.is_cuda and coord.is_cuda, "rdetr::two_stage_select: CUDA tensors only (no CPU path)")
+    _require(class_logits.dtype == torch.float32 and coord.dtype == torch.float32, "rdetr::two_stage_select: float32 inputs")
+    _require(class_logits.dim() == 3 and coord.dim() == 3 and coord.shape == (*class_logits.shape[:2], 4),
+             "rdetr::two_stage_select: class_logits [B, S, C] and coord [B, S, 4]")
+    cls, box = class_logits.contiguous(), coord.contiguous()
+    B, S, C = cls.shape
+    top_cls = torch.empty((B, k, C), dtype=torch.float32, device=cls.device)
+    top_box = torch.empty((B, k, 4), dtype=torch.float32, device=cls.device)
+    idx = torch.empty((B, k), dtype=torch.int64, device=cls.device)
+    L = _lib.lib()
+    nbytes = L.rdetr_two_stage_workspace_bytes(B, S)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cls.device)
+    with torch.cuda.device(cls.device):
+        rc = L.rdetr_two_stage_select(_ptr(cls), _ptr(box), B, S, C, int(k), 1 if sigmoid else 0, _ptr(top_cls), _ptr(top_box),
+                                      _ptr(idx), _ptr(ws), nbytes, _stream(cls))
+    _lib.check(rc, "rdetr_two_stage_select")
+    return top_cls, top_box, idx
+
+
+@two_stage_select_forward.register_fake
+def _(class_logits, coord, k, sigmoid):
+    B, S, C = class_logits.shape
+    return (class_logits.new_empty((B, k, C)), coord.new_empty((B, k, 4)),
+            torch.empty((B, k), dtype=torch.int64, device=class_logits.device))
+
+
+@torch.library.custom_op("rdetr::two_stage_select_backward", mutates_args=(), device_types="cuda")
+def two_stage_select_backward(grad_class: Tensor, grad_coord: Tensor, topk_coord: Tensor, topk_index: Tensor, S: int,
+                              sigmoid: bool) -> Tuple[Tensor, Tensor]:
+    B, K, C = grad_class.shape
+    gc, gb = grad_class.float().contiguous(), grad_coord.float().contiguous()
+    out_c = torch.empty((B, S, C), dtype=torch.float32, device=gc.device)
+    out_b = torch.empty((B, S, 4), dtype=torch.float32, device=gc.device)
+    with torch.cuda.device(gc.device):
+        rc = _lib.lib().rdetr_two_stage_select_backward(_ptr(gc), _ptr(gb), _ptr(topk_coord), _ptr(topk_index), B, S, C, K,
+                                                        1 if sigmoid else 0, _ptr(out_c), _ptr(out_b), _stream(gc))
+    _lib.check(rc, "rdetr_two_stage_select_backward")
+    return out_c, out_b
+
+
+@two_stage_select_backward.register_fake
+def _(grad_class, grad_coord, topk_coord, topk_index, S, sigmoid):
+    B, K, C = grad_class.shape
+    return grad_class.new_empty((B, S, C)), grad_coord.new_empty((B, S, 4))
+
+
+def _select_setup_context(ctx, inputs, output):
+    class_logits, coord, k, sigmoid = inputs
+    ctx.save_for_backward(output[1], output[2])
+    ctx.S, ctx.sigmoid = class_logits.shape[1], sigmoid
+    ctx.set_materialize_grads(True)
+
+
+def _select_autograd_backward(ctx, grad_class, grad_coord, grad_index):
+    topk_coord, topk_index = ctx.saved_tensors
+    gc, gb = two_stage_select_backward(grad_class, grad_coord, topk_coord, topk_index, ctx.S, ctx.sigmoid)
+    return gc, gb, None, None
+
+
+two_stage_select_forward.register_autograd(_select_autograd_backward, setup_context=_select_setup_context)
+
+
+def two_stage_select(class_logits: Tensor, coord_unact: Tensor, k: int, sigmoid: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """The reference's two-stage query selection (``relation_transformer.py:90-96`` / ``:104-111``) in three launches:
+    ``(class_logits.gather(topk rows), coord_unact.sigmoid().gather(topk rows), topk_index)`` with
+    ``topk_index = torch.topk(class_logits.max(-1)[0], k, dim=1)[1]``; differentiable in both inputs."""
+    top_cls, top_box, idx = two_stage_select_forward(class_logits.float(), coord_unact.float(), int(k), bool(sigmoid))
+    return top_cls.to(class_logits.dtype), top_box.to(coord_unact.dtype), idx
 
 
 # ---- batched linear-sum-assignment (SURVEY.md section 8, row N3) -------------------------------------
