@@ -28,6 +28,8 @@
 //     two-term Cody-Waite reduction followed by MUFU.SIN / MUFU.COS.
 // Both modes walk kRowsPerIter src rows per thread so that each shared-memory weight fetch feeds
 // kRowsPerIter * 4 FMAs.
+#include <stdlib.h>
+
 #include "rel_common.cuh"
 
 namespace rdetr {
@@ -434,6 +436,313 @@ rel_bwd_kernel(const float *__restrict__ src, const float *__restrict__ tgt, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FAST forward, round 2: the arithmetic of two src rows is packed into fp32x2 instructions (rel_common.cuh), the
+// epilogue addresses with one pointer per row and a constant head stride and stores under a predicate (the round-1
+// epilogue spent ~180 of ~850 instructions per pair on 64-bit index arithmetic and divergence bookkeeping).
+// CTA = 4 warps, tile = 32 tgt columns (lanes) x 64 src rows; a warp walks its 16 rows 2 * RP at a time.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_pred(float *p, float v, bool ok)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"((int)ok) : "memory");
+}
+
+template <int RP, bool MASKED>
+__global__ void __launch_bounds__(32 * kRelFwdWarps)
+rel_fwd_fast_kernel(const float *__restrict__ src_tab, const float *__restrict__ tgt_tab, const float *__restrict__ weight,
+                    const float *__restrict__ bias, const float *__restrict__ dim_t, float scale, const uint8_t *__restrict__ mask,
+                    float *__restrict__ out, uint32_t *__restrict__ relu_bits, int N1, int N2)
+{
+    __shared__ __align__(16) RelConsts rc;
+    __shared__ __align__(16) float2 s_row2[kFwdRowsPerCta / 2][kTab];
+    __shared__ float s_tgt[kTab][32];
+
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * 32 + lane;
+    const int b = blockIdx.z;
+    const int i_cta = blockIdx.y * kFwdRowsPerCta;
+    const int j = blockIdx.x * 32 + lane;
+    const bool jok = j < N2;
+    rel_consts_setup(rc, weight, bias, dim_t, tid, 32 * kRelFwdWarps);
+    stage_row_pairs(&s_row2[0][0], src_tab + ((size_t)b * N1 + i_cta) * kTab, min(kFwdRowsPerCta, N1 - i_cta), kFwdRowsPerCta, tid,
+                    32 * kRelFwdWarps);
+    {
+        const float *trow = tgt_tab + ((size_t)b * N2 + (jok ? j : 0)) * kTab;
+        for (int f = warp; f < kTab; f += kRelFwdWarps) s_tgt[f][lane] = __ldg(trow + f);
+    }
+    __syncthreads();
+
+    const int nwords = (N2 + 31) >> 5;
+    const size_t head_stride = (size_t)N1 * N2;
+    for (int r0 = 0; r0 < kFwdRowsPerWarp; r0 += 2 * RP) {
+        const int lrow = warp * kFwdRowsPerWarp + r0;  // row inside the CTA tile (even)
+        const int i0 = i_cta + lrow;
+        if (i0 >= N1) break;  // warp-uniform
+
+        f32x2 acc[RP][kRelHeads];
+        fast_bias_rows<RP>(rc, &s_row2[lrow >> 1][0], s_tgt, scale, lane, acc);
+
+        // ---- epilogue: ReLU, optional -inf mask, 1-bit sign record ----
+        float *prow = out + ((size_t)b * kRelHeads * N1 + i0) * N2 + j;
+#pragma unroll
+        for (int r = 0; r < 2 * RP; ++r) {
+            const int i = i0 + r;
+            const bool ok = jok && i < N1;
+            bool blocked = false;
+            if constexpr (MASKED) blocked = ok && mask[(size_t)i * N2 + j] != 0;
+            float *p = prow + (size_t)r * N2;
+            uint32_t words[kRelHeads];
+#pragma unroll
+            for (int h = 0; h < kRelHeads; ++h) {
+                float lo, hi;
+                unpack2(acc[r >> 1][h], lo, hi);
+                const float a = (r & 1) ? hi : lo;
+                // a blocked (masked_fill -inf) position gets no gradient, whatever the caller feeds back there:
+                // the reference's masked_fill_ cuts the graph at those elements (relation_transformer.py:372-374)
+                words[h] = __ballot_sync(0xffffffffu, ok && !blocked && a > 0.f);
+                st_global_pred(p, blocked ? -INFINITY : fmaxf(a, 0.f), ok);
+                p += head_stride;
+            }
+            if (relu_bits != nullptr && lane == 0 && i < N1) {
+                uint4 *dst = reinterpret_cast<uint4 *>(relu_bits + (((size_t)b * N1 + i) * nwords + blockIdx.x) * kRelHeads);
+                dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+                dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST backward, round 2.  Same decomposition as rel_bwd_kernel (8 warps walk the same pairs, warp w owns box feature
+// c = w / 2 and frequencies 4 * (w % 2) .. + 3: 8 features x 8 heads per lane; gradient tiles double buffered with
+// cp.async), but the 64 accumulators are 32 fp32x2 pairs {sin, cos} of one frequency:
+//   centre warps: the angle reduction runs packed over two FREQUENCIES ({chi_k, chi_k+1} are natural register pairs);
+//   size warps:   {sin(A-B), cos(A-B)} = {sA, cA} * {cB, cB} + {-cA, sA} * {sB, sB}: one packed mul + one packed fma,
+//                 the src side staged as float4 {sA, cA, -cA, sA} per (row, size feature, frequency);
+//   grad_weight:  acc2[h][k] += {g, g} * {sin, cos}: 32 packed FMAs per pair instead of 64 scalar ones.
+// Per-element operations and their order are those of the round-1 kernel.
+// Dynamic shared memory (kRelBwdFastSmem bytes): gradient tiles, ReLU words, staged src rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdFastTileRows = 32;   // half as many CTA barriers per pair as the 16-row tiles of rel_bwd_kernel
+struct RelBwdFastSmem {
+    float g[2][kBwdFastTileRows][kRelHeads][32];
+    float4 rowS[kBwdRowsPerCta][2][kRelK];   // {sA, cA, -cA, sA} per (row, w / h, k)
+    float4 geo[kBwdRowsPerCta];              // {cx, cy, 1 / (w + eps), 1 / (h + eps)}
+    uint32_t bits[2][kBwdFastTileRows][kRelHeads];
+};
+
+__global__ void __launch_bounds__(32 * kRelBwdWarps, 2)
+rel_bwd_fast_kernel(const float *__restrict__ src_tab, const float *__restrict__ tgt_tab, const float *__restrict__ dim_t, float scale,
+                    const float *__restrict__ grad_out, const uint32_t *__restrict__ relu_bits, float *__restrict__ grad_weight,
+                    float *__restrict__ grad_bias, int N1, int N2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RelBwdFastSmem &sm = *reinterpret_cast<RelBwdFastSmem *>(smem_raw);
+
+    const int lane = threadIdx.x;
+    const int w = threadIdx.y;
+    const int tid = w * 32 + lane;
+    const int c = w >> 1;  // box feature of this warp
+    const int k0 = (w & 1) * 4;
+    const int b = blockIdx.z;
+    const int j = blockIdx.x * 32 + lane;
+    const bool jok = j < N2;
+    const int nwords = (N2 + 31) >> 5;
+    const int i_cta = blockIdx.y * kBwdRowsPerCta;
+    const int nrows = min(kBwdRowsPerCta, N1 - i_cta);
+
+    {   // src rows: rows >= nrows hold 1.0 (harmless geometry; their gradient tile entries are zero)
+        const float *rows = src_tab + ((size_t)b * N1 + i_cta) * kTab;
+        for (int idx = tid; idx < kBwdRowsPerCta * 17; idx += 32 * kRelBwdWarps) {
+            const int r = idx / 17, e = idx - r * 17;
+            const bool valid = r < nrows;
+            const float *row = rows + (size_t)r * kTab;
+            if (e == 16) {
+                sm.geo[r] = valid ? make_float4(row[0], row[1], row[2], row[3]) : make_float4(1.f, 1.f, 1.f, 1.f);
+            } else {
+                const float sA = valid ? row[4 + e] : 1.f, cA = valid ? row[20 + e] : 1.f;   // e = (w / h) * 8 + k
+                sm.rowS[r][e >> 3][e & 7] = make_float4(sA, cA, -cA, sA);
+            }
+        }
+    }
+
+    // per-warp constants: centre warps the two frequency PAIRS (k0, k0+1), (k0+2, k0+3); size warps the tgt side
+    // (one register array for both roles: kc[0..1] = chi, kc[2..3] = -chi, kc[4..5] = clo  |  kc[0..3] = {cB, cB}, kc[4..7] = {sB, sB})
+    f32x2 kc[8];
+    float t_xy = 0.f;
+    {
+        const float *trow = tgt_tab + ((size_t)b * N2 + (jok ? j : 0)) * kTab;
+        if (c < 2) {
+            t_xy = __ldg(trow + c);
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                float h0, l0, h1, l1;
+                rev_constants(__ldg(dim_t + k0 + 2 * kp), h0, l0);
+                rev_constants(__ldg(dim_t + k0 + 2 * kp + 1), h1, l1);
+                kc[kp] = pack2(h0, h1);
+                kc[2 + kp] = pack2(-h0, -h1);
+                kc[4 + kp] = pack2(l0, l1);
+            }
+            kc[6] = kc[7] = 0ull;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float sB = __ldg(trow + 4 + (c & 1) * 8 + k0 + k), cB = __ldg(trow + 20 + (c & 1) * 8 + k0 + k);
+                kc[k] = pack2(cB, cB);
+                kc[4 + k] = pack2(sB, sB);
+            }
+        }
+    }
+    const f32x2 twopi2 = pack2(6.283185307179586f, 6.283185307179586f);
+    const f32x2 magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
+
+    f32x2 acc[kRelHeads][4];   // {sum g sin, sum g cos} of frequency k0 + k
+    float accb[kRelHeads];
+#pragma unroll
+    for (int h = 0; h < kRelHeads; ++h) {
+        accb[h] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[h][k] = 0ull;
+    }
+
+    auto issue_tile = [&](int t0, int buf) {
+        const int trows = min(kBwdFastTileRows, nrows - t0);
+        for (int r = 0; r < kBwdFastTileRows; ++r) {
+            float *dst = &sm.g[buf][r][w][lane];
+            if (r < trows && jok) {
+                const float *gsrc = grad_out + (((size_t)b * kRelHeads + w) * N1 + (i_cta + t0 + r)) * N2 + j;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(gsrc) : "memory");
+            } else {
+                *dst = 0.f;
+            }
+        }
+        if (tid < kBwdFastTileRows * kRelHeads) {
+            const int r = tid >> 3, h = tid & 7;
+            uint32_t *dst = &sm.bits[buf][r][h];
+            if (r < trows && relu_bits == nullptr) {
+                *dst = 0xffffffffu;  // gradient already gated by its producer (rel_attn.cu)
+            } else if (r < trows) {
+                const uint32_t *bsrc = relu_bits + (((size_t)b * N1 + (i_cta + t0 + r)) * nwords + blockIdx.x) * kRelHeads + h;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(bsrc) : "memory");
+            } else {
+                *dst = 0u;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue_tile(0, 0);
+    int buf = 0;
+    for (int t0 = 0; t0 < nrows; t0 += kBwdFastTileRows, buf ^= 1) {
+        const int trows = min(kBwdFastTileRows, nrows - t0);
+        if (t0 + kBwdFastTileRows < nrows) {
+            issue_tile(t0 + kBwdFastTileRows, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // tile `buf` (and, on the first pass, the staged rows) visible to every warp
+        // apply the ReLU mask once per CTA (warp w owns head w of the tile) instead of once per consumer warp
+#pragma unroll 4
+        for (int r = 0; r < kBwdFastTileRows; ++r) {
+            const float raw = sm.g[buf][r][w][lane];
+            sm.g[buf][r][w][lane] = ((sm.bits[buf][r][w] >> lane) & 1u) ? raw : 0.f;
+        }
+        __syncthreads();
+
+        // two rows per iteration (two independent feature chains in flight); rows past `trows` read zeroed gradients
+        for (int r = 0; r < trows; r += 2) {
+            f32x2 f2[2][4];
+            if (c < 2) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 geo = sm.geo[t0 + r + u];
+                    const float xy = c == 0 ? geo.x : geo.y, inv = c == 0 ? geo.z : geo.w;
+                    const float es = logf(fmaf(fabsf(xy - t_xy), inv, 1.0f)) * scale;
+                    const f32x2 es2 = pack2(es, es);
+#pragma unroll
+                    for (int kp = 0; kp < 2; ++kp) {
+                        const f32x2 nn2 = fadd2(fadd2(fmul2(es2, kc[2 + kp]), magic2), nmagic2);   // -rint(es * chi), see angle_sincos2
+                        f32x2 f = ffma2r(es2, kc[kp], nn2);
+                        f = ffma2r(es2, kc[4 + kp], f);
+                        float a0, a1;
+                        unpack2(fmul2(f, twopi2), a0, a1);
+                        f2[u][2 * kp] = pack2(__sinf(a0), __cosf(a0));
+                        f2[u][2 * kp + 1] = pack2(__sinf(a1), __cosf(a1));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const ulonglong2 A = *reinterpret_cast<const ulonglong2 *>(&sm.rowS[t0 + r + u][c & 1][k0 + k]);
+                        f2[u][k] = ffma2r(A.x, kc[k], fmul2(A.y, kc[4 + k]));   // {sA cB - cA sB, cA cB + sA sB}
+                    }
+            }
+#pragma unroll
+            for (int h = 0; h < kRelHeads; ++h) {
+                const float g0 = sm.g[buf][r][h][lane], g1 = sm.g[buf][r + 1][h][lane];
+                const f32x2 g02 = pack2(g0, g0), g12 = pack2(g1, g1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ffma2(acc[h][k], g02, f2[0][k]);
+                    ffma2(acc[h][k], g12, f2[1][k]);
+                }
+            }
+        }
+        if (w == 7) {  // grad_bias: one warp only, in a loop of its own (inside the loop above the compiler if-converts it for all 8 warps)
+            for (int r = 0; r < trows; r += 2)
+#pragma unroll
+                for (int h = 0; h < kRelHeads; ++h) accb[h] += sm.g[buf][r][h][lane] + sm.g[buf][r + 1][h][lane];
+        }
+        __syncthreads();  // every warp is done with tile `buf` before the copy after next overwrites it
+    }
+
+    // reduce over the 32 columns, then one atomic per (h, n) and warp
+#pragma unroll
+    for (int h = 0; h < kRelHeads; ++h) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float vs, vc;
+            unpack2(acc[h][k], vs, vc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                vs += __shfl_xor_sync(0xffffffffu, vs, off);
+                vc += __shfl_xor_sync(0xffffffffu, vc, off);
+            }
+            if (lane == 0) {
+                atomicAdd(grad_weight + h * kRelFeat + c * 2 * kRelK + 2 * (k0 + k), vs);
+                atomicAdd(grad_weight + h * kRelFeat + c * 2 * kRelK + 2 * (k0 + k) + 1, vc);
+            }
+        }
+        if (w == 7) {
+            float v = accb[h];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) atomicAdd(grad_bias + h, v);
+        }
+    }
+}
+
+// rows per thread and iteration of the FAST forward: 4 (default) or 8 (RDETR_REL_ROWS=8, tuning only)
+static int rel_fast_rows_per_iter()
+{
+    const char *e = getenv("RDETR_REL_ROWS");
+    return (e && e[0] == '8') ? 8 : 4;
+}
+
+template <int RP>
+static int launch_rel_fwd_fast(const float *ts, const float *tt, const float *weight, const float *bias, const float *dim_t, float scale,
+                               const uint8_t *mask, float *out, uint32_t *relu_bits, int B, int N1, int N2, cudaStream_t st)
+{
+    const dim3 block(32, kRelFwdWarps);
+    const dim3 grid((N2 + 31) / 32, (N1 + kFwdRowsPerCta - 1) / kFwdRowsPerCta, B);
+    if (mask) rel_fwd_fast_kernel<RP, true><<<grid, block, 0, st>>>(ts, tt, weight, bias, dim_t, scale, mask, out, relu_bits, N1, N2);
+    else rel_fwd_fast_kernel<RP, false><<<grid, block, 0, st>>>(ts, tt, weight, bias, dim_t, scale, nullptr, out, relu_bits, N1, N2);
+    return check_cuda(cudaGetLastError(), "rel_fwd_fast_kernel launch");
+}
+
 static int validate_rel(const char *who, int B, int N1, int N2, int H, int flags)
 {
     if (B < 0 || N1 < 0 || N2 < 0) return fail(RDETR_ERR_INVALID_ARGUMENT, "%s: negative size (B=%d N1=%d N2=%d)", who, B, N1, N2);
@@ -471,8 +780,10 @@ int launch_rel_bwd_fast(const float *src, const float *tgt, const float *src_tab
     const dim3 block(32, kRelBwdWarps);
     const dim3 grid((N2 + 31) / 32, (N1 + kBwdRowsPerCta - 1) / kBwdRowsPerCta, B);
     if (grid.y > 65535) return fail(RDETR_ERR_UNSUPPORTED, "relation backward: N1=%d too large", N1);
-    rel_bwd_kernel<true><<<grid, block, 0, st>>>(src, tgt, src_tab, tgt_tab, dim_t, scale, eps, grad, relu_bits, grad_weight, grad_bias,
-                                                 N1, N2);
+    if (int rc = check_cuda(cudaFuncSetAttribute(rel_bwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RelBwdFastSmem)),
+                            "cudaFuncSetAttribute(rel_bwd_fast)"))
+        return rc;
+    rel_bwd_fast_kernel<<<grid, block, sizeof(RelBwdFastSmem), st>>>(src_tab, tgt_tab, dim_t, scale, grad, relu_bits, grad_weight, grad_bias, N1, N2);
     return check_cuda(cudaGetLastError(), "rel_bwd_kernel launch");
 }
 
@@ -507,8 +818,8 @@ extern "C" int rdetr_relation_forward(const float *src_boxes, const float *tgt_b
         if (int rc = prepare_tables("rdetr_relation_forward", src_boxes, tgt_boxes, dim_t, scale, eps, B, N1, N2, workspace,
                                     workspace_bytes, st, &ts, &tt))
             return rc;
-        rel_fwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, ts, tt, weight, bias, dim_t, scale, eps, attn_mask, out,
-                                                     relu_bits, N1, N2);
+        return rel_fast_rows_per_iter() == 8 ? launch_rel_fwd_fast<4>(ts, tt, weight, bias, dim_t, scale, attn_mask, out, relu_bits, B, N1, N2, st)
+                                             : launch_rel_fwd_fast<2>(ts, tt, weight, bias, dim_t, scale, attn_mask, out, relu_bits, B, N1, N2, st);
     } else {
         rel_fwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, nullptr, nullptr, weight, bias, dim_t, scale, eps,
                                                       attn_mask, out, relu_bits, N1, N2);
@@ -542,8 +853,7 @@ extern "C" int rdetr_relation_backward(const float *src_boxes, const float *tgt_
         if (int rc = prepare_tables("rdetr_relation_backward", src_boxes, tgt_boxes, dim_t, scale, eps, B, N1, N2, workspace,
                                     workspace_bytes, st, &ts, &tt))
             return rc;
-        rel_bwd_kernel<true><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, ts, tt, dim_t, scale, eps, grad_out, relu_bits,
-                                                     grad_weight, grad_bias, N1, N2);
+        return launch_rel_bwd_fast(src_boxes, tgt_boxes, ts, tt, dim_t, scale, eps, grad_out, relu_bits, grad_weight, grad_bias, B, N1, N2, st);
     } else {
         rel_bwd_kernel<false><<<grid, block, 0, st>>>(src_boxes, tgt_boxes, nullptr, nullptr, dim_t, scale, eps, grad_out,
                                                       relu_bits, grad_weight, grad_bias, N1, N2);

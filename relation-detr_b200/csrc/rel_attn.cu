@@ -11,7 +11,7 @@
 //     out[b,h,i,:] = sum_j softmax_j( q[b,h,i,:].k[b,h,j,:] / sqrt(D) + relu(W[h,:].f(src_i, tgt_j) + c[h]) [-inf if masked] ) v[b,h,j,:]
 // and a CTA owns (image b, 32 query rows, all 8 heads):
 //   forward   per 32-key tile: (A) all 8 warps build the bias tile [8 heads][32 keys][32 rows] in shared memory with the
-//             FAST arithmetic of rel_fwd_kernel (per-box tables + angle-difference identities, MUFU for the centre
+//             FAST arithmetic of rel_fwd_fast_kernel (per-box tables + angle-difference identities, MUFU for the centre
 //             features, packed fma.rn.f32x2 projection -- the 64 geometry features of a pair are shared by the heads);
 //             (B) thread (row = lane, head = warp) runs an fp32 online softmax over the tile against K / V rows that all
 //             lanes of the warp read from shared memory as broadcasts.  Saves only the log-sum-exp per row.
@@ -33,83 +33,17 @@ constexpr int kAPad = 33;     // row pitch of the [head][key][row] tiles (confli
 constexpr int kAThreads = 32 * kRelHeads;
 
 struct AttnSmem {
-    float2 wt[kRelFeat][kRelHeads];   // projection weights, transposed and duplicated (rel.cu)
-    float row[kATI][kTab];            // FAST table rows of the CTA's query boxes (src)
+    RelConsts rc;                     // projection weights (transposed, duplicated), bias, angle constants (rel_common.cuh)
+    float2 row2[kATI / 2][kTab];      // FAST table rows of the CTA's query boxes (src), as row pairs
     float tgt[kTab][kATJ];            // FAST table rows of the tile's key boxes (tgt), [field][key]
-    float bias[kRelHeads];
-    float d[kRelK], invd[kRelK];      // (chi, clo) of 1 / (2 pi dim_t[k])
 };
-
-// Pre-activation of the relation bias for rows lrow .. lrow+3 of the CTA tile and key `lane` of the current tile, all 8
-// heads: the FAST branch of rel_fwd_kernel (rel.cu) with R = 4.  acc[p][h] = (row 2p, row 2p+1) of head h.
-__device__ __forceinline__ void fast_bias_rows4(const AttnSmem &sm, float scale, int lrow, int lane, f32x2 (&acc)[2][kRelHeads])
-{
-    constexpr int R = 4;
-#pragma unroll
-    for (int p = 0; p < R / 2; ++p)
-#pragma unroll
-        for (int h = 0; h < kRelHeads; ++h) acc[p][h] = pack2(sm.bias[h], sm.bias[h]);
-    const float x2 = sm.tgt[0][lane], y2 = sm.tgt[1][lane];
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {  // centre features
-        const float t_xy = c == 0 ? x2 : y2;
-        float es[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float *row = sm.row[lrow + r];
-            es[r] = logf(fmaf(fabsf(row[c] - t_xy), row[2 + c], 1.0f)) * scale;
-        }
-#pragma unroll 2
-        for (int k = 0; k < kRelK; ++k) {
-            float sn[R], cs[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) angle_sincos<true>(es[r], sm.d[k], sm.invd[k], sn[r], cs[r]);
-            project<R>(sm.wt, c * 2 * kRelK + 2 * k, sn, cs, acc);
-        }
-    }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {  // size features: per-box tables + angle-difference identities
-#pragma unroll 1
-        for (int k4 = 0; k4 < kRelK; k4 += 4) {
-            float4 sA4[R], cA4[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                sA4[r] = *reinterpret_cast<const float4 *>(&sm.row[lrow + r][4 + c * 8 + k4]);
-                cA4[r] = *reinterpret_cast<const float4 *>(&sm.row[lrow + r][20 + c * 8 + k4]);
-            }
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int k = k4 + kk;
-                const float sBk = sm.tgt[4 + c * 8 + k][lane], cBk = sm.tgt[20 + c * 8 + k][lane];
-                float sn[R], cs[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float sA = kk == 0 ? sA4[r].x : kk == 1 ? sA4[r].y : kk == 2 ? sA4[r].z : sA4[r].w;
-                    const float cA = kk == 0 ? cA4[r].x : kk == 1 ? cA4[r].y : kk == 2 ? cA4[r].z : cA4[r].w;
-                    sn[r] = fmaf(sA, cBk, -(cA * sBk));
-                    cs[r] = fmaf(cA, cBk, sA * sBk);
-                }
-                project<R>(sm.wt, (2 + c) * 2 * kRelK + 2 * k, sn, cs, acc);
-            }
-        }
-    }
-}
 
 // Per-CTA constants (all threads; caller syncs afterwards).
 __device__ __forceinline__ void attn_setup(AttnSmem &sm, const float *weight, const float *bias, const float *dim_t,
                                            const float *src_tab, int b, int i0, int N, int tid)
 {
-    for (int idx = tid; idx < kRelFeat * kRelHeads; idx += kAThreads) {
-        const int h = idx / kRelFeat, n = idx - h * kRelFeat;
-        const float wv = weight[idx];
-        sm.wt[n][h] = make_float2(wv, wv);
-    }
-    if (tid < kRelHeads) sm.bias[tid] = bias[tid];
-    if (tid < kRelK) rev_constants(dim_t[tid], sm.d[tid], sm.invd[tid]);
-    const float *rows = src_tab + ((size_t)b * N + i0) * kTab;
-    const int nvalid = min(kATI, N - i0) * kTab;
-    float *flat = &sm.row[0][0];
-    for (int idx = tid; idx < kATI * kTab; idx += kAThreads) flat[idx] = idx < nvalid ? rows[idx] : 1.0f;
+    rel_consts_setup(sm.rc, weight, bias, dim_t, tid, kAThreads);
+    stage_row_pairs(&sm.row2[0][0], src_tab + ((size_t)b * N + i0) * kTab, min(kATI, N - i0), kATI, tid, kAThreads);
 }
 
 // K / V rows and the key boxes' table rows of tile j0 -> shared memory (rows past N are zero / clamped).
@@ -138,7 +72,7 @@ __device__ __forceinline__ void attn_bias_tile(const AttnSmem &sm, float *s_pb, 
                                                int N, int lane, int warp)
 {
     f32x2 acc[2][kRelHeads];
-    fast_bias_rows4(sm, scale, warp * 4, lane, acc);
+    fast_bias_rows<2>(sm.rc, &sm.row2[warp * 2][0], sm.tgt, scale, lane, acc);   // rows warp * 4 .. + 3 of the CTA tile
     const int gj = j0 + lane;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

@@ -66,6 +66,159 @@ __device__ __forceinline__ void ffma2(f32x2 &acc, f32x2 a, f32x2 b)
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 ffma2r(f32x2 a, f32x2 b, f32x2 c)   // a * b + c
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 ld2(const float2 *p) { return *reinterpret_cast<const f32x2 *>(p); }
+
+// ---- FAST arithmetic on ROW PAIRS (round 2) ----------------------------------------------------------------------------
+// The forward kernels are issue bound, so everything that is the same operation on two src rows runs as ONE packed
+// fp32x2 instruction (mul / fma.rn.f32x2: two IEEE operations, per-element results unchanged): the Cody-Waite angle
+// reduction of the centre features, the angle-difference identities of the size features, and the projection.
+// Shared-memory layouts:
+//   row2[p][f]  = { table[2p][f], table[2p + 1][f] }   the FAST table rows (kTab fields) of two consecutive src boxes
+//   tgt[f][col] =   table[col][f]                      the table rows of the CTA's 32 tgt boxes, transposed
+struct RelConsts {                       // per-CTA constants
+    float2 wt[kRelFeat][kRelHeads];      // projection weights transposed and duplicated: [n][h] = {w, w}
+    float2 chi2[kRelK], nchi2[kRelK], clo2[kRelK];   // {c, c}, {-c, -c}: hi part of 1 / (2 pi dim_t[k]); {lo, lo}
+    float bias[kRelHeads];
+};
+
+__device__ __forceinline__ void rel_consts_setup(RelConsts &rc, const float *__restrict__ weight, const float *__restrict__ bias,
+                                                 const float *__restrict__ dim_t, int tid, int nthreads)
+{
+    for (int idx = tid; idx < kRelFeat * kRelHeads; idx += nthreads) {
+        const int h = idx / kRelFeat, n = idx - h * kRelFeat;
+        const float wv = weight[idx];
+        rc.wt[n][h] = make_float2(wv, wv);
+    }
+    if (tid < kRelHeads) rc.bias[tid] = bias[tid];
+    if (tid < kRelK) {
+        float chi, clo;
+        rev_constants(dim_t[tid], chi, clo);
+        rc.chi2[tid] = make_float2(chi, chi);
+        rc.nchi2[tid] = make_float2(-chi, -chi);
+        rc.clo2[tid] = make_float2(clo, clo);
+    }
+}
+
+// rows [0, nvalid) of `rows` (kTab floats each) -> row2[0 .. nrows / 2); rows past nvalid hold 1.0 (harmless geometry)
+__device__ __forceinline__ void stage_row_pairs(float2 *row2, const float *__restrict__ rows, int nvalid, int nrows, int tid, int nthreads)
+{
+    float *flat = reinterpret_cast<float *>(row2);
+    for (int idx = tid; idx < nrows * kTab; idx += nthreads) {
+        const int r = idx / kTab, f = idx - r * kTab;
+        flat[((r >> 1) * kTab + f) * 2 + (r & 1)] = r < nvalid ? rows[idx] : 1.0f;
+    }
+}
+
+// {sin, sin} and {cos, cos} of the angles es / d_k of two rows: angle_sincos<true> on both halves, bit for bit.
+// rint() is two packed additions of 1.5 * 2^23 (round-to-nearest-even at integer granularity, exact for |t| < 2^22; here
+// |t| = |es * chi| < 200) instead of two FRNDs on the 4-lane XU pipe, and it is applied to -t: rint(-t) = -rint(t).
+__device__ __forceinline__ void angle_sincos2(f32x2 es2, f32x2 chi2, f32x2 nchi2, f32x2 clo2, f32x2 twopi2, f32x2 magic2, f32x2 nmagic2,
+                                              f32x2 &sn2, f32x2 &cs2)
+{
+    const f32x2 nn2 = fadd2(fadd2(fmul2(es2, nchi2), magic2), nmagic2);   // -rint(es * chi)
+    f32x2 f = ffma2r(es2, chi2, nn2);
+    f = ffma2r(es2, clo2, f);
+    float a, b;
+    unpack2(fmul2(f, twopi2), a, b);
+    sn2 = pack2(__sinf(a), __sinf(b));
+    cs2 = pack2(__cosf(a), __cosf(b));
+}
+
+// acc[p][h] += W[h][n] * fs[p] + W[h][n + 1] * fc[p] (sin term first), fs / fc = the feature of rows (2p, 2p + 1)
+template <int RP>
+__device__ __forceinline__ void project2(const float2 (*wt)[kRelHeads], int n, const f32x2 (&fs)[RP], const f32x2 (&fc)[RP],
+                                         f32x2 (&acc)[RP][kRelHeads])
+{
+    const ulonglong2 *ws = reinterpret_cast<const ulonglong2 *>(&wt[n][0]);
+    const ulonglong2 *wc = reinterpret_cast<const ulonglong2 *>(&wt[n + 1][0]);
+#pragma unroll
+    for (int q = 0; q < kRelHeads / 2; ++q) {
+        const ulonglong2 w = ws[q];
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            ffma2(acc[p][2 * q], w.x, fs[p]);
+            ffma2(acc[p][2 * q + 1], w.y, fs[p]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kRelHeads / 2; ++q) {
+        const ulonglong2 w = wc[q];
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            ffma2(acc[p][2 * q], w.x, fc[p]);
+            ffma2(acc[p][2 * q + 1], w.y, fc[p]);
+        }
+    }
+}
+
+// Pre-activation of the relation bias for the 2 * RP src rows whose pairs start at `row2` and tgt column `lane`, all heads:
+// acc[p][h] = (row 2p, row 2p + 1) of head h.  Same per-element operations as the scalar FAST path of round 1; the 64 terms
+// are summed in the order (x, w, y, h) x k x (sin, cos).
+template <int RP>
+__device__ __forceinline__ void fast_bias_rows(const RelConsts &rc, const float2 *row2, const float (*tgt)[32], float scale, int lane,
+                                               f32x2 (&acc)[RP][kRelHeads])
+{
+#pragma unroll
+    for (int p = 0; p < RP; ++p)
+#pragma unroll
+        for (int h = 0; h < kRelHeads; ++h) acc[p][h] = pack2(rc.bias[h], rc.bias[h]);
+    const f32x2 twopi2 = pack2(6.283185307179586f, 6.283185307179586f);
+    const f32x2 magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f);
+    // One loop over (x / w, k) and (y / h, k): its body evaluates one CENTRE frequency (XU pipe: 4 MUFU per row pair) and one
+    // SIZE frequency (FMA pipe only) and projects both, so that every warp always has work for both pipes in flight.
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+        const float t_xy = tgt[c][lane];
+        f32x2 es2[RP];
+#pragma unroll
+        for (int p = 0; p < RP; ++p) {
+            const float2 xy = row2[p * kTab + c], inv = row2[p * kTab + 2 + c];
+            const float e0 = logf(fmaf(fabsf(xy.x - t_xy), inv.x, 1.0f)) * scale;  // (x * scale) first, position_encoding.py:133
+            const float e1 = logf(fmaf(fabsf(xy.y - t_xy), inv.y, 1.0f)) * scale;
+            es2[p] = pack2(e0, e1);
+        }
+#pragma unroll 2
+        for (int k = 0; k < kRelK; ++k) {
+            f32x2 fs[RP], fc[RP];
+            {   // centre feature c, frequency k
+                const f32x2 chi2 = ld2(&rc.chi2[k]), nchi2 = ld2(&rc.nchi2[k]), clo2 = ld2(&rc.clo2[k]);
+#pragma unroll
+                for (int p = 0; p < RP; ++p) angle_sincos2(es2[p], chi2, nchi2, clo2, twopi2, magic2, nmagic2, fs[p], fc[p]);
+                project2<RP>(rc.wt, c * 2 * kRelK + 2 * k, fs, fc, acc);
+            }
+            {   // size feature 2 + c, frequency k: per-box tables + angle-difference identities
+                const float sB = tgt[4 + c * 8 + k][lane], cB = tgt[20 + c * 8 + k][lane];
+                const f32x2 sB2 = pack2(sB, sB), nsB2 = pack2(-sB, -sB), cB2 = pack2(cB, cB);
+#pragma unroll
+                for (int p = 0; p < RP; ++p) {
+                    const f32x2 sA2 = ld2(&row2[p * kTab + 4 + c * 8 + k]), cA2 = ld2(&row2[p * kTab + 20 + c * 8 + k]);
+                    fs[p] = ffma2r(sA2, cB2, fmul2(cA2, nsB2));  // sin(A - B) = sA cB - cA sB
+                    fc[p] = ffma2r(cA2, cB2, fmul2(sA2, sB2));   // cos(A - B) = cA cB + sA sB
+                }
+                project2<RP>(rc.wt, (2 + c) * 2 * kRelK + 2 * k, fs, fc, acc);
+            }
+        }
+    }
+}
+
 // acc[p][h] = (row 2p, row 2p+1) of head h;  acc += W[h][n] * sn + W[h][n+1] * cs, sin term first.
 // Weights sit in shared memory transposed and duplicated: s_wt2[n][h] = {w, w}.
 template <int R>

@@ -1,8 +1,8 @@
 """Fused position-relation bias on the B200 vs the oracle (through the C ABI).
 
 Tolerances: EXACT mode forward max-abs <= 5e-5 vs the fp64 reference (the reference's own fp32 noise
-is up to 2e-5 on these cases, tests/golden/REPORT.txt) and mean-abs <= 2e-6; FAST mode <= 1e-4 /
-5e-6.  grad_weight / grad_bias: max-abs-error / max-abs-reference <= 2e-4 (fp32 atomics over up to
+is up to 2e-5 on these cases, tests/golden/REPORT.txt) and mean-abs <= 2e-6; FAST mode (the default) is pinned
+to what was measured (profiles/r01_rel_accuracy.json: 9.1e-6 .. 1.1e-5 max, 3.4e-7 mean): <= 3e-5 / 1e-6.  grad_weight / grad_bias: max-abs-error / max-abs-reference <= 2e-4 (fp32 atomics over up to
 6.5 M pairs; the reference's own fp32 noise on grad_weight is 3e-4..7e-4 absolute)."""
 import numpy as np
 import pytest
@@ -46,7 +46,7 @@ def test_matches_reference_fixtures(name, fast):
     ref = g["ref64_out_masked"] if mask is not None else g["ref64_out"]
     assert np.array_equal(np.isneginf(out), np.isneginf(ref))
     fin = np.isfinite(ref)
-    tol_max, tol_mean = (1e-4, 5e-6) if fast else (5e-5, 2e-6)
+    tol_max, tol_mean = (3e-5, 1e-6) if fast else (5e-5, 2e-6)
     assert maxabs(out[fin], ref[fin]) <= tol_max
     assert np.abs(out[fin] - ref[fin]).mean() <= tol_mean
     assert (out[fin] >= 0).all()
@@ -65,8 +65,8 @@ def test_matches_c_oracle_on_seeded_inputs(B, N1, N2):
     gw64, gb64 = c_oracle.rel_backward(*a64, dim_t, r["grad_output"].numpy().astype(np.float64))
     for fast in (False, True):
         out, gw, gb = run_ours(src, tgt, w, b, r["grad_output"], None, fast)
-        assert maxabs(out, o64) <= (1e-4 if fast else 5e-5), fast
-        assert np.abs(out - o64).mean() <= (5e-6 if fast else 2e-6), fast
+        assert maxabs(out, o64) <= (3e-5 if fast else 5e-5), fast
+        assert np.abs(out - o64).mean() <= (1e-6 if fast else 2e-6), fast
         # sign disagreements of the pre-activation can only happen within rounding of zero ...
         flips = (out > 0) != (o64 > 0)
         assert np.abs(o64[flips]).max(initial=0.0) <= 1e-4
