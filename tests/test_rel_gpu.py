@@ -172,6 +172,51 @@ def test_full_size_properties():
     assert d.max().item() <= 1e-4 and d.mean().item() <= 5e-6
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_full_size_b8_against_fp64_gpu_oracle(fast):
+    """BASELINE configs[2] at its FULL size (B = 8, N = 900, and N = 1100 with the CDN mask) against the eager port in float64
+    on the same device, one image at a time; forward and both parameter gradients.  VERDICT r1 weak #2."""
+    for name, dn in (("rel_900_b8", 0), ("rel_1100_b8", 200)):
+        shape = workloads.REL_SHAPES[name]
+        r = workloads.make_rel_inputs(shape, seed=0, device=DEV)
+        mask = workloads.cdn_attn_mask(shape.n1 - dn, 10, dn // 10, DEV) if dn else None
+        go = r["grad_output"] if mask is None else r["grad_output"].masked_fill(mask, 0.0)
+        w = r["weight"].clone().requires_grad_(True)
+        b = r["bias"].clone().requires_grad_(True)
+        out = ops.position_relation_bias(r["src_boxes"], r["tgt_boxes"], w, b, attn_mask=mask, fast=fast)
+        keep = out.detach().clone()
+        out.backward(go)
+        w64 = r["weight"].double().requires_grad_(True)
+        b64 = r["bias"].double().requires_grad_(True)
+        worst_max, sum_abs, count = 0.0, 0.0, 0
+        slack = torch.zeros(8, dtype=torch.float64, device=DEV)   # per head: sum of |grad_out| over ReLU sign disagreements
+        for i in range(shape.batch):
+            o64 = torch_port.rel_eager(r["src_boxes"][i:i + 1].double(), r["tgt_boxes"][i:i + 1].double(), w64, b64)
+            o64.backward(go[i:i + 1].double())
+            got = keep[i:i + 1]
+            if mask is not None:
+                assert torch.isneginf(got[..., mask]).all()
+                d = (got.double() - o64.detach())[..., ~mask].abs()
+            else:
+                d = (got.double() - o64.detach()).abs()
+            worst_max, sum_abs, count = max(worst_max, d.max().item()), sum_abs + d.sum().item(), count + d.numel()
+            flips = (got > 0) != (o64.detach() > 0)
+            if mask is not None:
+                flips &= ~mask   # blocked positions are -inf on our side by construction; their gradient is zeroed on both sides
+            assert (o64.detach().abs() * flips).max().item() <= 1e-4   # ... which only happen within rounding of zero
+            slack += (go[i:i + 1].double().abs() * flips).sum(dim=(0, 2, 3))
+            del o64, d, flips
+        tol_max, tol_mean = (3e-5, 1e-6) if fast else (5e-5, 2e-6)
+        print(f"\n{name} fast={fast}: max {worst_max:.2e} mean {sum_abs / count:.2e}")
+        assert worst_max <= tol_max and sum_abs / count <= tol_mean, (name, worst_max, sum_abs / count)
+        # each ReLU sign flip moves grad_weight[h, :] / grad_bias[h] by up to |grad_out| (|f| <= 1): per-head slack, as in the
+        # seeded test above; the rest is fp32 accumulation over 6.5 M (9.7 M) pairs against float64
+        gw_err = (w.grad.double().reshape(8, 64) - w64.grad.reshape(8, 64)).abs().amax(dim=1)
+        gb_err = (b.grad.double() - b64.grad).abs()
+        assert (gw_err <= 5e-4 * w64.grad.abs().max() + slack).all(), (name, gw_err.tolist(), slack.tolist())
+        assert (gb_err <= 5e-4 * b64.grad.abs().max() + slack).all(), (name, gb_err.tolist(), slack.tolist())
+
+
 def test_focal_config_size_properties():
     """B=1, N=2900 (focalnet config with denoising_nums=1000): sub-block consistency, mask fusion, backward."""
     r = workloads.make_rel_inputs(workloads.REL_SHAPES["rel_2900_b1"], seed=0, device=DEV)
