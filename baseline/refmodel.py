@@ -87,9 +87,11 @@ def set_reference_extension(mode: str = "none") -> str:
 
 def build_relation_detr_r50(num_classes: int = 91, num_queries: int = 900, hybrid_num_proposals: int = 1500,
                             enc_layers: int = 6, dec_layers: int = 6, num_feature_levels: int = 4, denoising_nums: int = 100,
-                            min_size: int = 800, max_size: int = 1333):
+                            min_size: int = 800, max_size: int = 1333, backbone_name: str = "resnet50"):
     """RelationDETR R50 as configs/relation_detr/relation_detr_resnet50_800_1333.py builds it, random init.
-    Call ``relation_detr_b200.install.install()`` BEFORE this to get the B200 operators inside."""
+    Call ``relation_detr_b200.install.install()`` BEFORE this to get the B200 operators inside.
+    ``backbone_name="focalnet_large_lrf_fl4"`` swaps in the backbone line of
+    configs/relation_detr/relation_detr_focalnet_large_lrf_fl4_1200_2000.py:35 (see ``build_relation_detr_focal_l``)."""
     activate()
     from torch import nn
 
@@ -105,7 +107,12 @@ def build_relation_detr_r50(num_classes: int = 91, num_queries: int = 900, hybri
 
     embed_dim, num_heads, dim_feedforward, hybrid_assign = 256, 8, 2048, 6
     position_embedding = PositionEmbeddingSine(embed_dim // 2, temperature=10000, normalize=True, offset=-0.5)
-    backbone = ResNetBackbone("resnet50", weights=False, norm_layer=FrozenBatchNorm2d, return_indices=(1, 2, 3), freeze_indices=(0,))
+    if backbone_name == "resnet50":
+        backbone = ResNetBackbone("resnet50", weights=False, norm_layer=FrozenBatchNorm2d, return_indices=(1, 2, 3), freeze_indices=(0,))
+    else:
+        from models.backbones.focalnet import FocalNetBackbone
+
+        backbone = FocalNetBackbone(backbone_name, weights=False, return_indices=(0, 1, 2, 3))
     neck = ChannelMapper(in_channels=backbone.num_channels, out_channels=embed_dim, num_outs=num_feature_levels)
     transformer = rt.RelationTransformer(
         encoder=rt.RelationTransformerEncoder(
@@ -135,6 +142,14 @@ def build_relation_detr_r50(num_classes: int = 91, num_queries: int = 900, hybri
                          criterion=criterion, postprocessor=postprocessor, num_classes=num_classes, num_queries=num_queries,
                          hybrid_assign=hybrid_assign, denoising_nums=denoising_nums, min_size=min_size, max_size=max_size)
     return model, weight_dict
+
+
+def build_relation_detr_focal_l(enc_layers: int = 6, dec_layers: int = 6):
+    """BASELINE configs[4]: RelationDETR with the FocalNet-L backbone, 5 feature levels, 1200x2000 images and
+    denoising_nums = 1000, as configs/relation_detr/relation_detr_focalnet_large_lrf_fl4_1200_2000.py builds it
+    (:24 num_feature_levels = 5, :35 backbone with weights=False, :101-103 denoising_nums / min_size / max_size)."""
+    return build_relation_detr_r50(enc_layers=enc_layers, dec_layers=dec_layers, num_feature_levels=5, denoising_nums=1000,
+                                   min_size=1200, max_size=2000, backbone_name="focalnet_large_lrf_fl4")
 
 
 def synthetic_batch(batch: int, device, seed: int = 0, height: int = 800, width: int = 1333, boxes_per_image: int = 10,

@@ -40,7 +40,9 @@ def _max_over_ranks(x: float, dev) -> float:
 
 
 def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int = 2, height: int = 800, width: int = 1333,
-        boxes_per_image: int = 10, enc_layers: int = 6, dec_layers: int = 6, log_sync: bool = False, profile_share: bool = False) -> dict:
+        boxes_per_image: int = 10, enc_layers: int = 6, dec_layers: int = 6, log_sync: bool = False, profile_share: bool = False,
+        model_name: str = "r50") -> dict:
+    """``model_name="focal_l"`` = BASELINE configs[4] (FocalNet-L, 5 levels; call it with height=1200, width=2000, batch 1)."""
     import torch
     import torch.distributed as dist
 
@@ -62,7 +64,10 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
         if path == "reference_cuda" and ext != "prebuilt":
             return {"unavailable": "oracle/_ref (the reference's own CUDA kernel, prebuilt) is not present"}
     torch.manual_seed(0)
-    model, _ = refmodel.build_relation_detr_r50(enc_layers=enc_layers, dec_layers=dec_layers)
+    if model_name == "focal_l":
+        model, _ = refmodel.build_relation_detr_focal_l(enc_layers=enc_layers, dec_layers=dec_layers)
+    else:
+        model, _ = refmodel.build_relation_detr_r50(enc_layers=enc_layers, dec_layers=dec_layers)
     if path not in ("ours_fused_attention", "ours_all"):  # the lazy relation-bias hand-over is a class-level switch: it stays on while the model runs
         rinstall.uninstall()
     model = model.to(dev).train()
@@ -91,7 +96,7 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
     ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev)
-    res = {"path": path, "precision": precision, "msda_path": ext, "ms_per_step": round(ms, 2), "host_ms_per_step": round(wall_ms, 2),
+    res = {"path": path, "model": model_name, "precision": precision, "msda_path": ext, "ms_per_step": round(ms, 2), "host_ms_per_step": round(wall_ms, 2),
            "imgs_per_s": round(world * batch_per_gpu / ms * 1e3, 2), "global_batch": world * batch_per_gpu, "steps": steps, "warmup": warmup,
            "loss": round(float(loss), 4), "params_M": round(n_params / 1e6, 2),
            "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2)}
@@ -154,6 +159,9 @@ if __name__ == "__main__":
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
     if path == "cpu":
         print(json.dumps(cpu_inference(1)))
+    elif len(sys.argv) > 3 and sys.argv[3] == "focal_l":   # BASELINE configs[4]
+        torch.cuda.set_device(0)
+        print(json.dumps(run(path, prec, 3, 2, batch_per_gpu=1, height=1200, width=2000, profile_share=True, model_name="focal_l")))
     else:
         torch.cuda.set_device(0)
         print(json.dumps(run(path, prec, 5, 2, profile_share=True)))

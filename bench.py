@@ -630,6 +630,18 @@ def run_train_block(args, world, rank, quick: bool):
                 extra[key] = train_bench.run(path, prec, max(3, k // 2), 2)
             except Exception as e:  # noqa: BLE001
                 extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if not quick and world == 1:
+        # BASELINE configs[4]: FocalNet-L, 5 levels, 1200x2000, batch 1, denoising_nums = 1000 -- the reference's own classes again
+        focal = {"model": "Relation-DETR FocalNet-L (focalnet_large_lrf_fl4, reference classes, random init), 1200x2000, 5 levels, batch 1, "
+                          "denoising_nums 1000, AdamW + clip 0.1 (BASELINE configs[4])"}
+        for key, path, prec in (("fp32", "ours", "fp32"), ("bf16", "ours", "bf16"), ("reference_path_fp32", "reference", "fp32"),
+                                ("reference_cuda_kernel_fp32", "reference_cuda", "fp32")):
+            try:
+                focal[key] = train_bench.run(path, prec, 3, 2, batch_per_gpu=1, height=1200, width=2000, model_name="focal_l",
+                                             profile_share=(path == "ours"))
+            except Exception as e:  # noqa: BLE001
+                focal[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        train["focal_l_1200x2000"] = focal
     return train, extra
 
 
