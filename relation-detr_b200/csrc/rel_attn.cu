@@ -22,6 +22,8 @@
 //             workspace for grad_weight / grad_bias.  (That hand-over still writes dS once; the forward bias, its
 //             masked copy and SDPA's reads of both are gone.)
 // CUDA cores, fp32 throughout: the 1e-4 gradient tolerance of the north star rules out tf32 / bf16 products here.
+#include <stdlib.h>
+
 #include "rel_common.cuh"
 
 namespace rdetr {
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(kAThreads, 2)
 relattn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
                    const float *__restrict__ src_tab, const float *__restrict__ tgt_tab, const float *__restrict__ weight,
                    const float *__restrict__ bias, const float *__restrict__ dim_t, float scale,
-                   const uint8_t *__restrict__ mask, float *__restrict__ out, float *__restrict__ lse, int N, float sm_scale)
+                   const uint8_t *__restrict__ mask, float *__restrict__ out, float *__restrict__ lse, int N, float sm_scale,
+                   int tiles_per_split, float *__restrict__ part_o, float *__restrict__ part_ml)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AttnSmem &sm = *reinterpret_cast<AttnSmem *>(smem_raw);
@@ -121,7 +124,9 @@ relattn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
     float m = -INFINITY, l = 0.f;
     __syncthreads();
 
-    for (int j0 = 0; j0 < N; j0 += kATJ) {
+    // key split (small grids, e.g. the training shape B = 2): blockIdx.z owns the key tiles [jbeg, jend)
+    const int jbeg = blockIdx.z * tiles_per_split * kATJ, jend = min(N, jbeg + tiles_per_split * kATJ);
+    for (int j0 = jbeg; j0 < jend; j0 += kATJ) {
         attn_load_tile(sm, s_k4, s_v4, k, v, tgt_tab, b, j0, N, tid, lane, warp);
         __syncthreads();
         attn_bias_tile(sm, s_pb, scale, mask, i0, j0, N, lane, warp);
@@ -170,7 +175,13 @@ relattn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
         }
         __syncthreads();  // the next tile overwrites K / V / bias
     }
-    if (rowok) {
+    if (rowok && part_o != nullptr) {  // one of several key splits: unnormalised partial, merged by relattn_combine_kernel
+        const size_t prow = (((size_t)blockIdx.z * gridDim.y + b) * kRelHeads + warp) * N + gi;
+        float4 *o4 = reinterpret_cast<float4 *>(part_o) + prow * (kAD / 4);
+#pragma unroll
+        for (int c = 0; c < kAD / 4; ++c) o4[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        reinterpret_cast<float2 *>(part_ml)[prow] = make_float2(m, l);
+    } else if (rowok) {
         const float inv = 1.0f / l;  // l == 0 (every key blocked) -> NaN row, as torch's softmax of an all -inf row
         float4 *o4 = reinterpret_cast<float4 *>(out) + (((size_t)b * kRelHeads + warp) * N + gi) * (kAD / 4);
 #pragma unroll
@@ -179,13 +190,39 @@ relattn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
     }
 }
 
+// Merges the key splits of the forward: out = sum_s o_s e^(m_s - m) / sum_s l_s e^(m_s - m), lse = m + log(sum ...), m = max_s m_s.
+// One thread per (image, head, row, 4 channels); `rows` = B * H * N.
+__global__ void __launch_bounds__(256)
+relattn_combine_kernel(const float *__restrict__ part_o, const float *__restrict__ part_ml, float *__restrict__ out,
+                       float *__restrict__ lse, long long rows, int splits)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = idx >> 3;
+    const int c = (int)(idx & 7);
+    if (row >= rows) return;
+    float m = -INFINITY;
+    for (int s = 0; s < splits; ++s) m = fmaxf(m, reinterpret_cast<const float2 *>(part_ml)[(size_t)s * rows + row].x);
+    float l = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        const float2 ml = reinterpret_cast<const float2 *>(part_ml)[(size_t)s * rows + row];
+        const float w = ml.x == -INFINITY ? 0.f : __expf(ml.x - m);   // a split whose keys are all blocked contributes nothing
+        const float4 o = reinterpret_cast<const float4 *>(part_o)[((size_t)s * rows + row) * (kAD / 4) + c];
+        l = fmaf(ml.y, w, l);
+        acc.x = fmaf(o.x, w, acc.x); acc.y = fmaf(o.y, w, acc.y); acc.z = fmaf(o.z, w, acc.z); acc.w = fmaf(o.w, w, acc.w);
+    }
+    const float inv = 1.0f / l;  // every key of the row blocked: 0 * inf = NaN, as the unsplit kernel and torch's softmax
+    reinterpret_cast<float4 *>(out)[row * (kAD / 4) + c] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    if (c == 0) lse[row] = m + logf(l);
+}
+
 __global__ void __launch_bounds__(kAThreads, 1)
 relattn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
                    const float *__restrict__ src_tab, const float *__restrict__ tgt_tab, const float *__restrict__ weight,
                    const float *__restrict__ bias, const float *__restrict__ dim_t, float scale,
                    const uint8_t *__restrict__ mask, const float *__restrict__ out, const float *__restrict__ lse,
                    const float *__restrict__ gout, float *__restrict__ dq, float *__restrict__ dk, float *__restrict__ dv,
-                   float *__restrict__ dS, int N, float sm_scale)
+                   float *__restrict__ dS, int N, float sm_scale, int tiles_per_split)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AttnSmem &sm = *reinterpret_cast<AttnSmem *>(smem_raw);
@@ -227,7 +264,8 @@ relattn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
     const float row_lse = rowok ? __ldg(lse + rowoff) : INFINITY;
     __syncthreads();
 
-    for (int j0 = 0; j0 < N; j0 += kATJ) {
+    const int jbeg = blockIdx.z * tiles_per_split * kATJ, jend = min(N, jbeg + tiles_per_split * kATJ);   // key split, as the forward
+    for (int j0 = jbeg; j0 < jend; j0 += kATJ) {
         attn_load_tile(sm, s_k4, s_v4, k, v, tgt_tab, b, j0, N, tid, lane, warp);
         __syncthreads();
         attn_bias_tile(sm, s_pb, scale, mask, i0, j0, N, lane, warp);
@@ -319,7 +357,12 @@ relattn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
         }
         __syncthreads();  // the next tile overwrites K / V / bias
     }
-    if (rowok) {
+    if (rowok && gridDim.z > 1) {  // key splits add their share of dq (zero-filled by the caller)
+#pragma unroll
+        for (int c = 0; c < kAD / 4; ++c)
+            red_add_f32x4(dq + rowoff * kAD + 4 * c, dqv[4 * c] * sm_scale, dqv[4 * c + 1] * sm_scale, dqv[4 * c + 2] * sm_scale,
+                          dqv[4 * c + 3] * sm_scale);
+    } else if (rowok) {
         float4 *d4 = reinterpret_cast<float4 *>(dq) + rowoff * (kAD / 4);
 #pragma unroll
         for (int c = 0; c < kAD / 4; ++c)
@@ -329,6 +372,35 @@ relattn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k, con
 
 static size_t fwd_smem_bytes() { return ((sizeof(AttnSmem) + 15) & ~size_t(15)) + 2 * kRelHeads * kATJ * kAD * sizeof(float) + kRelHeads * kATJ * kAPad * sizeof(float); }
 static size_t bwd_smem_bytes() { return ((sizeof(AttnSmem) + 15) & ~size_t(15)) + 4 * kRelHeads * kATJ * kAD * sizeof(float) + 2 * kRelHeads * kATJ * kAPad * sizeof(float); }
+
+// Key splits for small grids (B200: 148 SMs; the forward keeps 2 CTAs per SM resident, the backward 1).  The grid is
+// B x ceil(N / 32) CTAs: 232 at B = 8, N = 900 (no split) but 70 at the training shape B = 2, N = 1100 and 91 at B = 1, N = 2900.
+constexpr int kSmCount = 148;
+constexpr int kMaxSplits = 8;
+static int attn_splits(int B, int N, bool backward)
+{
+    const int tiles = (N + kATJ - 1) / kATJ;
+    const long long ctas = (long long)B * ((N + kATI - 1) / kATI);
+    if (const char *e = getenv("RDETR_RELATTN_SPLITS")) {   // tuning / tests: force a split count
+        const int v = atoi(e);
+        if (v >= 1) return v < tiles ? (v < kMaxSplits ? v : kMaxSplits) : tiles;
+    }
+    // time ~ waves x (key tiles per CTA + ~2 tiles' worth of per-CTA setup) + a little per split for the merge / the dq
+    // reductions; fewest splits among the best
+    const long long slots = backward ? kSmCount : 2 * kSmCount;
+    int best = 1;
+    double best_cost = 0.0;
+    for (int ks = 1; ks <= kMaxSplits && ks <= tiles; ++ks) {
+        const long long waves = (ctas * ks + slots - 1) / slots;
+        const double cost = (double)waves * ((tiles + ks - 1) / ks + 2) + 0.5 * (ks - 1);
+        if (ks == 1 || cost < best_cost - 1e-9) { best = ks; best_cost = cost; }
+    }
+    return best;
+}
+static size_t attn_partial_bytes(int B, int N, int H, int splits)
+{
+    return splits > 1 ? (size_t)splits * B * H * N * (kAD + 2) * sizeof(float) : 0;
+}
 
 static int validate_attn(const char *who, int B, int N, int H, int D)
 {
@@ -347,6 +419,7 @@ extern "C" size_t rdetr_relation_attention_workspace_bytes(int B, int N, int H, 
     size_t bytes = rdetr_relation_workspace_bytes(B, N, N, RDETR_REL_FAST);
     bytes = (bytes + 255) & ~size_t(255);
     if (backward) bytes += (size_t)B * H * N * N * sizeof(float);  // the gated score gradient handed to rel_bwd_kernel
+    else bytes += rdetr::attn_partial_bytes(B, N, H, rdetr::kMaxSplits);   // partial outputs of the forward's key splits
     return bytes;
 }
 
@@ -374,10 +447,27 @@ extern "C" int rdetr_relation_attention_forward(const float *q, const float *k, 
     if (int rc = check_cuda(cudaFuncSetAttribute(relattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(relattn_fwd)"))
         return rc;
-    const dim3 block(32, kRelHeads), grid((N + kATI - 1) / kATI, B);
+    const int splits = attn_splits(B, N, false);
+    const int tiles = (N + kATJ - 1) / kATJ, tiles_per_split = (tiles + splits - 1) / splits;
+    float *part_o = nullptr, *part_ml = nullptr;
+    if (splits > 1) {
+        const size_t tab_bytes = (rdetr_relation_workspace_bytes(B, N, N, RDETR_REL_FAST) + 255) & ~size_t(255);
+        if (workspace_bytes < tab_bytes + attn_partial_bytes(B, N, H, splits))
+            return fail(RDETR_ERR_WORKSPACE, "rdetr_relation_attention_forward: workspace of %zu bytes required, got %zu",
+                        rdetr_relation_attention_workspace_bytes(B, N, H, 0), workspace_bytes);
+        part_o = reinterpret_cast<float *>(static_cast<unsigned char *>(workspace) + tab_bytes);
+        part_ml = part_o + (size_t)splits * B * H * N * kAD;
+    }
+    const dim3 block(32, kRelHeads), grid((N + kATI - 1) / kATI, B, splits);
     relattn_fwd_kernel<<<grid, block, smem, st>>>(q, k, v, ts, tt, weight, bias, dim_t, scale, attn_mask, out, lse, N,
-                                                  1.0f / sqrtf((float)D));
-    return check_cuda(cudaGetLastError(), "relattn_fwd_kernel launch");
+                                                  1.0f / sqrtf((float)D), tiles_per_split, part_o, part_ml);
+    if (int rc = check_cuda(cudaGetLastError(), "relattn_fwd_kernel launch")) return rc;
+    if (splits > 1) {
+        const long long rows = (long long)B * H * N;
+        relattn_combine_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(part_o, part_ml, out, lse, rows, splits);
+        return check_cuda(cudaGetLastError(), "relattn_combine_kernel launch");
+    }
+    return RDETR_OK;
 }
 
 extern "C" int rdetr_relation_attention_backward(const float *q, const float *k, const float *v, const float *src_boxes,
@@ -418,9 +508,13 @@ extern "C" int rdetr_relation_attention_backward(const float *q, const float *k,
     if (int rc = check_cuda(cudaFuncSetAttribute(relattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(relattn_bwd)"))
         return rc;
-    const dim3 block(32, kRelHeads), grid((N + kATI - 1) / kATI, B);
+    const int splits = attn_splits(B, N, true);
+    const int tiles = (N + kATJ - 1) / kATJ, tiles_per_split = (tiles + splits - 1) / splits;
+    if (splits > 1)
+        if (int rc = check_cuda(cudaMemsetAsync(grad_q, 0, kv_bytes, st), "cudaMemsetAsync(grad_q)")) return rc;
+    const dim3 block(32, kRelHeads), grid((N + kATI - 1) / kATI, B, splits);
     relattn_bwd_kernel<<<grid, block, smem, st>>>(q, k, v, ts, tt, weight, bias, dim_t, scale, attn_mask, out, lse, grad_out, grad_q,
-                                                  grad_k, grad_v, dS, N, 1.0f / sqrtf((float)D));
+                                                  grad_k, grad_v, dS, N, 1.0f / sqrtf((float)D), tiles_per_split);
     if (int rc = check_cuda(cudaGetLastError(), "relattn_bwd_kernel launch")) return rc;
     // grad_weight / grad_bias from the gated score gradient (relu_bits = nullptr: already gated)
     return launch_rel_bwd_fast(src_boxes, tgt_boxes, ts, tt, dim_t, scale, eps, dS, nullptr, grad_weight, grad_bias, B, N, N, st);

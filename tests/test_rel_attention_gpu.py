@@ -90,6 +90,32 @@ def test_matches_the_unfused_pipeline_at_decoder_sizes(B, N, masked):
         assert _rel(got, ref) <= tol, (name, _rel(got, ref))
 
 
+@pytest.mark.parametrize("B,N,dn", [(1, 70, 40), (2, 333, 40), (1, 1100, 200)])
+def test_key_splits_agree_with_the_unsplit_kernel(B, N, dn, monkeypatch):
+    """Small grids split the keys over up to 4 CTAs per row block (forward: partial (o, m, l) merged by relattn_combine_kernel;
+    backward: dq by reductions).  Every split count must give the unsplit result up to summation order -- including rows for which
+    a whole split is blocked by the denoising mask (N = 70, dn = 40: keys 0..31 are one split, blocked for rows >= 40)."""
+    g = torch.Generator(device=DEV).manual_seed(N + dn)
+    q, k, v = (torch.randn((B, 8, N, 32), device=DEV, generator=g) for _ in range(3))
+    src, tgt = workloads.make_boxes(B, N, 1, DEV), workloads.make_boxes(B, N, 2, DEV)
+    w, b = workloads.make_rel_params(8, 64, 0, DEV)
+    mask = workloads.cdn_attn_mask(N - dn, 10, dn // 10, DEV)
+    go = torch.randn((B, 8, N, 32), device=DEV, generator=g)
+    runs = {}
+    for splits in (1, 2, 3, 4):
+        monkeypatch.setenv("RDETR_RELATTN_SPLITS", str(splits))
+        tq, tk, tv, tw, tb = (x.clone().requires_grad_(True) for x in (q, k, v, w, b))
+        out = ops.relation_attention(tq, tk, tv, src, tgt, tw, tb, attn_mask=mask)
+        out.backward(go)
+        runs[splits] = (out.detach(), tq.grad, tk.grad, tv.grad, tw.grad, tb.grad)
+    monkeypatch.delenv("RDETR_RELATTN_SPLITS")
+    assert torch.isfinite(runs[1][0]).all()
+    for splits in (2, 3, 4):
+        assert (runs[splits][0] - runs[1][0]).abs().max().item() <= 2e-6, splits
+        for got, ref, name in zip(runs[splits][1:], runs[1][1:], ("grad_q", "grad_k", "grad_v", "grad_weight", "grad_bias")):
+            assert _rel(got, ref) <= 2e-5, (splits, name, _rel(got, ref))
+
+
 def test_opcheck_and_errors():
     g = torch.Generator(device=DEV).manual_seed(0)
     q, k, v = (torch.randn((1, 8, 40, 32), device=DEV, generator=g).requires_grad_(True) for _ in range(3))

@@ -26,7 +26,7 @@ def timed(fn, warm=3, iters=10):
 
 
 def main():
-    for B, N, dn in ((8, 900, 0), (8, 1100, 200), (1, 2900, 2000)):
+    for B, N, dn in ((8, 900, 0), (8, 1100, 200), (2, 1100, 200), (1, 2900, 2000)):   # (2, 1100) = the training shape per GPU
         g = torch.Generator(device=DEV).manual_seed(0)
         q, k, v = (torch.randn((B, 8, N, 32), device=DEV, generator=g).requires_grad_(True) for _ in range(3))
         src, tgt = workloads.make_boxes(B, N, 1, DEV), workloads.make_boxes(B, N, 2, DEV)
