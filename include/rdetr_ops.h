@@ -189,7 +189,9 @@ int rdetr_relation_backward(const float *src_boxes, const float *tgt_boxes, cons
  *   lse         [B, H, N] fp32: log-sum-exp of every row, the only thing the backward needs besides the inputs and out
  *   grad_q / grad_k / grad_v like q; grad_weight [H, 64], grad_bias [H]: all ZEROED INSIDE the backward call
  *   workspace   rdetr_relation_attention_workspace_bytes(B, N, H, backward) bytes: per-box tables, plus -- backward only --
- *               one [B, H, N, N] fp32 buffer through which the ReLU-gated score gradient reaches the relation backward
+ *               one [B, H, N, N] fp32 buffer through which the ReLU-gated score gradient reaches the relation backward,
+ *               plus -- forward only, small grids -- the partial (o, m, l) of the key splits (B * ceil(N/32) CTAs would
+ *               not fill the 148 SMs at the training shape B = 2; up to 8 CTAs then share the keys of a row block)
  * Supported: H == 8, D == 32.  A row whose keys are all blocked yields NaN, as torch's softmax does.
  */
 size_t rdetr_relation_attention_workspace_bytes(int B, int N, int H, int backward);

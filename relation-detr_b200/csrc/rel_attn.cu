@@ -419,7 +419,7 @@ extern "C" size_t rdetr_relation_attention_workspace_bytes(int B, int N, int H, 
     size_t bytes = rdetr_relation_workspace_bytes(B, N, N, RDETR_REL_FAST);
     bytes = (bytes + 255) & ~size_t(255);
     if (backward) bytes += (size_t)B * H * N * N * sizeof(float);  // the gated score gradient handed to rel_bwd_kernel
-    else bytes += rdetr::attn_partial_bytes(B, N, H, rdetr::kMaxSplits);   // partial outputs of the forward's key splits
+    else bytes += rdetr::attn_partial_bytes(B, N, H, rdetr::attn_splits(B, N, false));   // partial outputs of the forward's key splits
     return bytes;
 }
 
