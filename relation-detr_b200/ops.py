@@ -73,6 +73,18 @@ def _check_msda_inputs(value, spatial_shapes, level_start_index, sampling_locati
     return B, S, M, D, L, Nq, P
 
 
+def _grad_like_param(g: Tensor, shape) -> Tensor:
+    """``g`` ([H, 64]) viewed with the parameter's shape AND the canonical contiguous strides of that shape: a plain
+    ``view`` to [H, 64, 1, 1] keeps stride 64 on the size-1 dims, which DDP's reducer reports as a layout mismatch with its
+    bucket view ("grad strides do not match bucket view strides") and handles by an extra copy."""
+    shape = tuple(shape)
+    strides, acc = [], 1
+    for n in reversed(shape):
+        strides.append(acc)
+        acc *= max(int(n), 1)
+    return g.as_strided(shape, tuple(reversed(strides)))
+
+
 # ---- MSDA ---------------------------------------------------------------------------------------
 
 @torch.library.custom_op("rdetr::msda_forward", mutates_args=(), device_types="cuda")
@@ -345,7 +357,7 @@ def _rel_autograd_backward(ctx, grad_out, grad_bits):
     src_boxes, tgt_boxes, dim_t, bits = ctx.saved_tensors
     gw, gb = relation_backward(src_boxes, tgt_boxes, dim_t, ctx.scale, ctx.eps, grad_out, bits, ctx.num_heads, ctx.fast)
     # no gradient reaches the boxes: the reference computes the geometry under no_grad (:527-529)
-    return None, None, gw.view(ctx.weight_shape), gb, None, None, None, None, None
+    return None, None, _grad_like_param(gw, ctx.weight_shape), gb, None, None, None, None, None
 
 
 relation_forward.register_autograd(_rel_autograd_backward, setup_context=_rel_setup_context)
@@ -447,7 +459,7 @@ def _relattn_autograd_backward(ctx, grad_out, grad_lse):
     gq, gk, gv, gw, gb = relation_attention_backward(q, k, v, src_boxes, tgt_boxes, weight, bias, dim_t, ctx.scale, ctx.eps,
                                                      ctx.attn_mask, out, lse, grad_out)
     # no gradient reaches the boxes: the reference computes the geometry under no_grad (relation_transformer.py:527-529)
-    return gq, gk, gv, None, None, gw.view(ctx.weight_shape), gb, None, None, None, None
+    return gq, gk, gv, None, None, _grad_like_param(gw, ctx.weight_shape), gb, None, None, None, None
 
 
 relation_attention_forward.register_autograd(_relattn_autograd_backward, setup_context=_relattn_setup_context)
