@@ -189,6 +189,135 @@ memfuse_kernel(const __grid_constant__ MfMaps maps, const float *__restrict__ bi
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kMfBN) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... with a 4-stage operand ring that runs
+// on ACROSS tiles and TWO 256-column accumulators in TMEM (all 512 columns): while warps 2-5 drain accumulator (i & 1) of tile i
+// (tcgen05.ld -> bias -> ReLU -> stores), warp 1 is already issuing the MMAs of tile i + 1 into the other one.  The 2-CTA-per-SM
+// kernel above gets its overlap from the second resident CTA but leaves each CTA only 2 stages (96 KB) of loads in flight.
+// Barriers: full / empty per stage (TMA <-> MMA), tmem_full / tmem_empty per accumulator (MMA <-> epilogue; tmem_empty counts
+// the four epilogue warps).
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kMfPStages = 4;
+
+__global__ void __launch_bounds__(kMfThreads, 1)
+memfuse_persistent_kernel(const __grid_constant__ MfMaps maps, const float *__restrict__ bias, float *__restrict__ out, int M, int nsrc,
+                          int kb_per_src, int src_cols, int relu, int ntiles)
+{
+    extern __shared__ unsigned char mf_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)mf_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kMfPStages], empty_bar[kMfPStages], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = nsrc * kb_per_src;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kMfPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the allocating warp also deallocates; 512 columns = the whole TMEM of the SM (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2u * kMfBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer: one continuous stream of k-blocks over all tiles of this CTA -------
+            uint32_t g = 0;  // running k-block counter
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = tile * kMfBM;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % kMfPStages;
+                    const uint32_t ph = (g / kMfPStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);  // passes at once on a fresh barrier
+                    mbar_expect_tx(&full_bar[s], kMfStageBytes);
+                    const int src = kb / kb_per_src, kc = kb - src * kb_per_src;
+                    unsigned char *st = tiles + (size_t)s * kMfStageBytes;
+                    tma_load_2d(st, &maps.a[src], kc * kMfBK, m0, &full_bar[s]);
+                    tma_load_2d(st + kMfBytesA, &maps.w, src * src_cols + kc * kMfBK, 0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer --------------------------------------------------------------------
+            uint32_t g = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (fresh: passes)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_addr = tmem_base + (uint32_t)(acc * kMfBN);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % kMfPStages;
+                    const uint32_t ph = (g / kMfPStages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * kMfStageBytes);
+                    const uint32_t b_addr = a_addr + kMfBytesA;
+#pragma unroll
+                    for (int k = 0; k < kMfBK / kMfUmmaK; ++k) {
+                        const uint64_t adesc = umma_desc_k_sw128(a_addr + k * kMfUmmaK * 4);
+                        const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * kMfUmmaK * 4);
+                        const uint32_t accumulate = (kb | k) != 0 ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(d_addr), "l"(adesc), "l"(bdesc), "r"(kMfIdesc), "r"(accumulate) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar[acc])) : "memory");
+            }
+        }
+    } else {
+        // ---- epilogue: warp w may address TMEM lanes 32 (w % 4) .. + 31 -------------------------------------------
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = tile * kMfBM + quarter * 32 + lane;
+            float *orow = out + (size_t)row * kMfBN;
+#pragma unroll 1
+            for (int cc = 0; cc < kMfBN / 32; ++cc) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * kMfBN + cc * 32);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc == kMfBN / 32 - 1) {
+                    // every column of this accumulator is in registers: hand it back to the MMA warp before the stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+                }
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + cc * 32 + j));
+                        float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                               __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        *reinterpret_cast<float4 *>(orow + cc * 32 + j) = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kMfBN) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -247,9 +376,20 @@ extern "C" int rdetr_memory_fusion_forward(const float *const *sources, int nsrc
     for (int t = 0; t < nsrc; ++t)
         if (int rc = make_map(&maps.a[t], sources[t], (uint64_t)M, (uint64_t)C, (uint64_t)C, kMfBM)) return rc;
     if (int rc = make_map(&maps.w, weight, (uint64_t)N, (uint64_t)nsrc * C, (uint64_t)nsrc * C, kMfBN)) return rc;
-    static const int stages = [] { const char *e = getenv("RDETR_MEMFUSE_STAGES"); const int v = e ? atoi(e) : 0; return v == 4 ? 4 : 2; }();
+    // RDETR_MEMFUSE_STAGES: 0 (default) = persistent kernel (1 CTA / SM, 4 stages, two TMEM accumulators);
+    // 2 = one tile per CTA, 2 CTAs / SM, 2 stages; 4 = one tile per CTA, 1 CTA / SM, 4 stages (A/B measurements)
+    static const int stages = [] { const char *e = getenv("RDETR_MEMFUSE_STAGES"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 2) ? v : 0; }();
     const unsigned grid = (unsigned)((M + kMfBM - 1) / kMfBM);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (stages == 0) {
+        const size_t smem = (size_t)kMfPStages * kMfStageBytes + 1024;
+        if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(memfuse)")) return rc;
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned ctas = grid < (unsigned)sms ? grid : (unsigned)sms;
+        memfuse_persistent_kernel<<<ctas, kMfThreads, smem, st>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu, (int)grid);
+        return check_cuda(cudaGetLastError(), "memfuse_persistent_kernel launch");
+    }
     const size_t smem = (size_t)stages * kMfStageBytes + 1024;
     if (stages == 4) {
         if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(memfuse)")) return rc;
