@@ -318,6 +318,141 @@ memfuse_persistent_kernel(const __grid_constant__ MfMaps maps, const float *__re
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kMfBN) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Persistent variant with 256-row super-tiles: the two TMEM accumulators hold the two 128-row halves of ONE tile, so a stage
+// carries A [256 x 32] + W [256 x 32] = 64 KB for 8 MMAs (8 KB per MMA instead of 12 KB: every W byte that crosses the L2 -> SM
+// fabric is used by twice as many rows).  The epilogue drains accumulator 0, hands it back, then accumulator 1; the MMA warp
+// of the next tile needs accumulator 1 only after its first four MMAs, so what is lost of the overlap is about one drain per tile.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kMfWStages = 3;
+constexpr uint32_t kMfWideStageBytes = 2 * kMfBytesA + kMfBytesB;   // 64 KB
+
+__global__ void __launch_bounds__(kMfThreads, 1)
+memfuse_wide_kernel(const __grid_constant__ MfMaps maps, const float *__restrict__ bias, float *__restrict__ out, int M, int nsrc,
+                    int kb_per_src, int src_cols, int relu, int ntiles)
+{
+    extern __shared__ unsigned char mf_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)mf_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kMfWStages], empty_bar[kMfWStages], tmem_full_bar, tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = nsrc * kb_per_src;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kMfWStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) mbar_init(&tmem_empty_bar[a], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2u * kMfBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer ------------------------------------------------------------------
+            uint32_t g = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = tile * 2 * kMfBM;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % kMfWStages;
+                    const uint32_t ph = (g / kMfWStages) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], kMfWideStageBytes);
+                    const int src = kb / kb_per_src, kc = kb - src * kb_per_src;
+                    unsigned char *st = tiles + (size_t)s * kMfWideStageBytes;
+                    tma_load_2d(st, &maps.a[src], kc * kMfBK, m0, &full_bar[s]);   // box of 256 rows: both halves, 16 KB apart
+                    tma_load_2d(st + 2 * kMfBytesA, &maps.w, src * src_cols + kc * kMfBK, 0, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer --------------------------------------------------------------------
+            uint32_t g = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t drained = (uint32_t)(it & 1) ^ 1u;   // parity of "the epilogue of the previous tile has drained it"
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % kMfWStages;
+                    const uint32_t ph = (g / kMfWStages) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * kMfWideStageBytes);
+                    const uint32_t b_addr = a_addr + 2 * kMfBytesA;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        if (kb == 0) {
+                            mbar_wait(&tmem_empty_bar[half], drained);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        const uint32_t d_addr = tmem_base + (uint32_t)(half * kMfBN);
+#pragma unroll
+                        for (int k = 0; k < kMfBK / kMfUmmaK; ++k) {
+                            const uint64_t adesc = umma_desc_k_sw128(a_addr + half * kMfBytesA + k * kMfUmmaK * 4);
+                            const uint64_t bdesc = umma_desc_k_sw128(b_addr + k * kMfUmmaK * 4);
+                            const uint32_t accumulate = (kb | k) != 0 ? 1u : 0u;
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                         ::"r"(d_addr), "l"(adesc), "l"(bdesc), "r"(kMfIdesc), "r"(accumulate) : "memory");
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tmem_full_bar)) : "memory");
+            }
+        }
+    } else {
+        // ---- epilogue: warp w may address TMEM lanes 32 (w % 4) .. + 31 of both accumulators ---------------------
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(&tmem_full_bar, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int row = tile * 2 * kMfBM + half * kMfBM + quarter * 32 + lane;
+                float *orow = out + (size_t)row * kMfBN;
+#pragma unroll 1
+                for (int cc = 0; cc < kMfBN / 32; ++cc) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kMfBN + cc * 32);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                                 : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cc == kMfBN / 32 - 1) {  // this accumulator is in registers: hand it back before the stores
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[half])) : "memory");
+                    }
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + cc * 32 + j));
+                            float4 v = make_float4(__uint_as_float(r[j]) + bv.x, __uint_as_float(r[j + 1]) + bv.y,
+                                                   __uint_as_float(r[j + 2]) + bv.z, __uint_as_float(r[j + 3]) + bv.w);
+                            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4 *>(orow + cc * 32 + j) = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kMfBN) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -343,9 +478,15 @@ static int make_map(CUtensorMap *map, const float *base, uint64_t rows, uint64_t
     const cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)kMfBK, box_rows};
     const cuuint32_t estr[2] = {1, 1};
+    // L2 promotion: a 128-byte box row is one k-block of a source row; promoting the fill to 256 bytes would bring the NEXT
+    // k-block of the same row into L2 with the same DRAM access -- measured: no difference (RDETR_MEMFUSE_L2PROMO = 64 / 128 / 256)
+    static const CUtensorMapL2promotion promo = [] {
+        const char *e = getenv("RDETR_MEMFUSE_L2PROMO");
+        const int v = e ? atoi(e) : 128;
+        return v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }();
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RDETR_ERR_CUDA, "memory_fusion: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return RDETR_OK;
 }
@@ -371,14 +512,15 @@ extern "C" int rdetr_memory_fusion_forward(const float *const *sources, int nsrc
     if (bits & 15) return fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_memory_fusion_forward: buffers must be 16-byte aligned");
     const DeviceGuard guard(out);
     if (guard.status()) return guard.status();
+    // RDETR_MEMFUSE_STAGES: 0 (default) = persistent kernel (1 CTA / SM, 4 stages, two TMEM accumulators = two tiles in flight);
+    // 8 = persistent kernel with 256-row super-tiles (two accumulators = two halves of one tile, W traffic halved per row);
+    // 2 = one tile per CTA, 2 CTAs / SM, 2 stages; 4 = one tile per CTA, 1 CTA / SM, 4 stages (A/B measurements)
+    static const int stages = [] { const char *e = getenv("RDETR_MEMFUSE_STAGES"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 2 || v == 8) ? v : 0; }();
     MfMaps maps;
     memset(&maps, 0, sizeof(maps));
     for (int t = 0; t < nsrc; ++t)
-        if (int rc = make_map(&maps.a[t], sources[t], (uint64_t)M, (uint64_t)C, (uint64_t)C, kMfBM)) return rc;
+        if (int rc = make_map(&maps.a[t], sources[t], (uint64_t)M, (uint64_t)C, (uint64_t)C, stages == 8 ? 2 * kMfBM : kMfBM)) return rc;
     if (int rc = make_map(&maps.w, weight, (uint64_t)N, (uint64_t)nsrc * C, (uint64_t)nsrc * C, kMfBN)) return rc;
-    // RDETR_MEMFUSE_STAGES: 0 (default) = persistent kernel (1 CTA / SM, 4 stages, two TMEM accumulators);
-    // 2 = one tile per CTA, 2 CTAs / SM, 2 stages; 4 = one tile per CTA, 1 CTA / SM, 4 stages (A/B measurements)
-    static const int stages = [] { const char *e = getenv("RDETR_MEMFUSE_STAGES"); const int v = e ? atoi(e) : 0; return (v == 4 || v == 2) ? v : 0; }();
     const unsigned grid = (unsigned)((M + kMfBM - 1) / kMfBM);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (stages == 0) {
@@ -389,6 +531,16 @@ extern "C" int rdetr_memory_fusion_forward(const float *const *sources, int nsrc
         const unsigned ctas = grid < (unsigned)sms ? grid : (unsigned)sms;
         memfuse_persistent_kernel<<<ctas, kMfThreads, smem, st>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu, (int)grid);
         return check_cuda(cudaGetLastError(), "memfuse_persistent_kernel launch");
+    }
+    if (stages == 8) {
+        const size_t smem = (size_t)kMfWStages * kMfWideStageBytes + 1024;
+        if (int rc = check_cuda(cudaFuncSetAttribute(memfuse_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(memfuse)")) return rc;
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned wide_tiles = (unsigned)((M + 2 * kMfBM - 1) / (2 * kMfBM));
+        const unsigned ctas = wide_tiles < (unsigned)sms ? wide_tiles : (unsigned)sms;
+        memfuse_wide_kernel<<<ctas, kMfThreads, smem, st>>>(maps, bias, out, (int)M, nsrc, C / kMfBK, C, relu, (int)wide_tiles);
+        return check_cuda(cudaGetLastError(), "memfuse_wide_kernel launch");
     }
     const size_t smem = (size_t)stages * kMfStageBytes + 1024;
     if (stages == 4) {
