@@ -732,6 +732,7 @@ def run_ours(args):
         guarded("gpu_baselines", lambda: gpu_side_baselines(torch, ops, workloads, inp, k))
         guarded("relation_attention_b8_n900", lambda: time_relation_attention(torch, ops, workloads, 8, 900, 0, k, w))
         guarded("relation_attention_b8_n1100_masked", lambda: time_relation_attention(torch, ops, workloads, 8, 1100, 200, k, w))
+        guarded("relation_attention_b2_n1100_masked_training_shape", lambda: time_relation_attention(torch, ops, workloads, 2, 1100, 200, k, w))
         guarded("memory_fusion_b8", lambda: time_memory_fusion(torch, ops, 8, shape.S, k, w, peak))
         guarded("two_stage_select_b8", lambda: time_two_stage(torch, ops, 8, shape.S, 900, k, w, peak))
         guarded("two_stage_select_1200x2000_b1", lambda: time_two_stage(torch, ops, 1, workloads.MSDA_SHAPES["msda_enc_1200x2000_b1"].S, 900, k, w, peak))
