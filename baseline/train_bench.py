@@ -54,6 +54,9 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     rank = dist.get_rank() if world > 1 else 0
     refmodel.activate()
     rinstall.uninstall()
+    graphed = path == "ours_graphed"   # "ours" + CUDA-graph capture of backbone / encoder / decoder passes (relation_detr_b200.graphs)
+    if graphed:
+        path = "ours"
     if path in ("ours", "ours_fused_attention", "ours_all"):
         report = rinstall.install(fused_attention=(path in ("ours_fused_attention", "ours_all")), fused_memory=(path == "ours_all"),
                                   fused_topk=(path == "ours_all"))
@@ -73,14 +76,19 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     model = model.to(dev).train()
     n_params = sum(p.numel() for p in model.parameters())
     train_model = model
+    amp = torch.bfloat16 if precision == "bf16" else None
+    images, targets = refmodel.synthetic_batch(batch_per_gpu, dev, seed=rank, height=height, width=width, boxes_per_image=boxes_per_image)
+    handle = None
+    if graphed:
+        from relation_detr_b200 import graphs
+
+        handle = graphs.capture_static_parts(model, images, targets, autocast_dtype=amp)
     if world > 1:
         train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index], find_unused_parameters=False)
     opt = train_step.build_optimizer(model)
-    images, targets = refmodel.synthetic_batch(batch_per_gpu, dev, seed=rank, height=height, width=width, boxes_per_image=boxes_per_image)
-    amp = torch.bfloat16 if precision == "bf16" else None
 
     def step():
-        return train_step.train_step(train_model, images, targets, opt, autocast_dtype=amp, log_sync=log_sync)
+        return train_step.train_step(train_model, images, targets, opt, autocast_dtype=amp, log_sync=log_sync, autocast_cache=not graphed)
 
     for _ in range(warmup):
         loss = step()
@@ -96,7 +104,7 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
     ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev)
-    res = {"path": path, "model": model_name, "precision": precision, "msda_path": ext, "ms_per_step": round(ms, 2), "host_ms_per_step": round(wall_ms, 2),
+    res = {"path": "ours_graphed" if graphed else path, "model": model_name, "precision": precision, "msda_path": ext, "ms_per_step": round(ms, 2), "host_ms_per_step": round(wall_ms, 2),
            "imgs_per_s": round(world * batch_per_gpu / ms * 1e3, 2), "global_batch": world * batch_per_gpu, "steps": steps, "warmup": warmup,
            "loss": round(float(loss), 4), "params_M": round(n_params / 1e6, 2),
            "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2)}
@@ -114,6 +122,9 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
                                         "device_busy_ms": round(tot / 1e3, 2)}
         except Exception as e:  # noqa: BLE001  (diagnostic only)
             res["kernel_time_share"] = {"error": f"{type(e).__name__}: {e}"[:160]}
+    if handle is not None:
+        res["graphed_parts"] = list(handle.parts)
+        handle.release()
     del opt, train_model, model
     rinstall.uninstall()
     torch.cuda.empty_cache()

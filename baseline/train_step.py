@@ -20,11 +20,13 @@ def build_optimizer(model, lr: float = 1e-4, weight_decay: float = 1e-4):
     return torch.optim.AdamW(groups, lr=lr, weight_decay=weight_decay, betas=(0.9, 0.999))
 
 
-def train_step(model, images, targets, optimizer, autocast_dtype=None, max_norm: float = 0.1, log_sync: bool = False):
-    """One optimisation step; returns the detached total loss (a 0-d tensor on the device)."""
+def train_step(model, images, targets, optimizer, autocast_dtype=None, max_norm: float = 0.1, log_sync: bool = False,
+               autocast_cache: bool = True):
+    """One optimisation step; returns the detached total loss (a 0-d tensor on the device).  ``autocast_cache=False`` is what
+    CUDA-graph-captured parts need under autocast (relation_detr_b200.graphs)."""
     import torch
 
-    ctx = torch.autocast("cuda", dtype=autocast_dtype) if autocast_dtype is not None else contextlib.nullcontext()
+    ctx = torch.autocast("cuda", dtype=autocast_dtype, cache_enabled=autocast_cache) if autocast_dtype is not None else contextlib.nullcontext()
     with ctx:
         loss_dict = model(images, targets)
         losses = sum(loss for loss in loss_dict.values())

@@ -618,6 +618,18 @@ def run_train_block(args, world, rank, quick: bool):
             train[prec] = train_bench.run("ours", prec, k, 3, profile_share=(world == 1 and not quick))
         except Exception as e:  # noqa: BLE001
             train[prec] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    # the same step with the static-shape parts (backbone, encoder, both decoder passes) captured in CUDA graphs, forward and
+    # backward (relation_detr_b200/graphs.py): the eager numbers above stay the headline of this block, these show what the
+    # launch-bound step gains once ~30 % of its launches are replayed
+    for prec in ("fp32", "bf16"):
+        try:
+            train[prec + "_graphed"] = train_bench.run("ours_graphed", prec, k, 3)
+        except Exception as e:  # noqa: BLE001
+            train[prec + "_graphed"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if "imgs_per_s" in train.get("fp32_graphed", {}):
+        train["imgs_per_s_graphed"] = train["fp32_graphed"]["imgs_per_s"]
+    if "imgs_per_s" in train.get("bf16_graphed", {}):
+        train["imgs_per_s_bf16_graphed"] = train["bf16_graphed"]["imgs_per_s"]
     if "imgs_per_s" in train.get("fp32", {}):
         train["imgs_per_s"] = train["fp32"]["imgs_per_s"]
         train["ms_per_step"] = train["fp32"]["ms_per_step"]
