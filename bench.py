@@ -608,6 +608,12 @@ def run_train_block(args, world, rank, quick: bool):
     if not refmodel.available():
         return {"unavailable": "baseline/_ref (the reference tree) is not installed: run python baseline/install_reference.py"}, {}
     k = max(3, min(args.steps, 10))
+    import gc
+
+    import torch
+
+    gc.collect()
+    torch.cuda.empty_cache()   # the operator extras leave gigabytes of odd-sized blocks in the caching allocator
     train = {"model": "Relation-DETR ResNet-50 (reference classes from baseline/_ref, random init), 800x1333, batch 2 per GPU, "
                       "AdamW + clip 0.1, DDP/NCCL gradient all-reduce" if world > 1 else
                       "Relation-DETR ResNet-50 (reference classes from baseline/_ref, random init), 800x1333, batch 2, AdamW + clip 0.1",
