@@ -131,6 +131,59 @@ def run(path: str, precision: str, steps: int, warmup: int, batch_per_gpu: int =
     return res
 
 
+def gpu_inference(path: str = "ours", precision: str = "fp32", passes: int = 10, warmup: int = 3, height: int = 800, width: int = 1333) -> dict:
+    """The recipe of tools/benchmark_model.py:26-61 (eval, ``eval_transform = None``, batch 1, inference_mode) on the GPU:
+    latency of one whole-model forward for the given operator path (``ours`` / ``reference`` / ``reference_cuda``)."""
+    import torch
+
+    from baseline import refmodel
+    from relation_detr_b200 import install as rinstall
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    refmodel.activate()
+    rinstall.uninstall()
+    graphed = path == "ours_graphed"
+    if path in ("ours", "ours_graphed"):
+        rinstall.install()
+        ext = "rdetr"
+    else:
+        ext = refmodel.set_reference_extension("prebuilt" if path == "reference_cuda" else "none")
+        if path == "reference_cuda" and ext != "prebuilt":
+            return {"unavailable": "oracle/_ref (the reference's own CUDA kernel, prebuilt) is not present"}
+    torch.manual_seed(0)
+    model, _ = refmodel.build_relation_detr_r50()
+    rinstall.uninstall()
+    model.eval_transform = None
+    model = model.to(dev).eval()
+    image = torch.randn(3, height, width, device=dev)
+    amp = torch.bfloat16 if precision == "bf16" else None
+    handle = None
+    if graphed:
+        from relation_detr_b200 import graphs
+
+        handle = graphs.capture_static_parts(model, (image,), None, autocast_dtype=amp)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=amp, enabled=amp is not None, cache_enabled=not graphed):
+        for _ in range(warmup):
+            model((image,))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(passes):
+            model((image,))
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3 / passes
+    ms = e0.elapsed_time(e1) / passes
+    if handle is not None:
+        handle.release()
+    res = {"path": path, "precision": precision, "msda_path": ext, "ms_per_image": round(ms, 2), "host_ms_per_image": round(wall, 2),
+           "imgs_per_s": round(1e3 / ms, 2), "passes": passes, "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2**30, 2)}
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def cpu_inference(passes: int = 3, height: int = 800, width: int = 1333) -> dict:
     """BASELINE.json configs[0]: whole Relation-DETR R50, eval, batch 1, synthetic 800x1333 image, on the host cores
     through the reference's own CPU path (recipe of tools/benchmark_model.py:26-61: eval_transform = None,
@@ -170,6 +223,9 @@ if __name__ == "__main__":
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
     if path == "cpu":
         print(json.dumps(cpu_inference(1)))
+    elif len(sys.argv) > 3 and sys.argv[3] == "infer":
+        torch.cuda.set_device(0)
+        print(json.dumps(gpu_inference(path, prec)))
     elif len(sys.argv) > 3 and sys.argv[3] == "focal_l":   # BASELINE configs[4]
         torch.cuda.set_device(0)
         print(json.dumps(run(path, prec, 3, 2, batch_per_gpu=1, height=1200, width=2000, profile_share=True, model_name="focal_l")))

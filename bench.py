@@ -649,6 +649,17 @@ def run_train_block(args, world, rank, quick: bool):
             except Exception as e:  # noqa: BLE001
                 extra[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if not quick and world == 1:
+        # whole-model inference on the GPU, the recipe of tools/benchmark_model.py (configs[0] is its CPU twin in cpu_baseline)
+        infer = {"workload": "Relation-DETR R50 800x1333 inference, batch 1, eval, random init, synthetic image, GPU"}
+        for key, path, prec in (("fp32", "ours", "fp32"), ("bf16", "ours", "bf16"), ("fp32_graphed", "ours_graphed", "fp32"),
+                                ("bf16_graphed", "ours_graphed", "bf16"), ("reference_path_fp32", "reference", "fp32"),
+                                ("reference_cuda_kernel_fp32", "reference_cuda", "fp32")):
+            try:
+                infer[key] = train_bench.gpu_inference(path, prec)
+            except Exception as e:  # noqa: BLE001
+                infer[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        extra["inference_r50_b1"] = infer
+    if not quick and world == 1:
         # BASELINE configs[4]: FocalNet-L, 5 levels, 1200x2000, batch 1, denoising_nums = 1000 -- the reference's own classes again
         focal = {"model": "Relation-DETR FocalNet-L (focalnet_large_lrf_fl4, reference classes, random init), 1200x2000, 5 levels, batch 1, "
                           "denoising_nums 1000, AdamW + clip 0.1 (BASELINE configs[4])"}

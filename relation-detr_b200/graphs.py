@@ -17,6 +17,10 @@ and rebinds ``module.forward`` on the instances.  Constraints (those of partial-
 fixed number of denoising queries (the synthetic benchmark; production data needs one capture per shape bucket), the same
 ``requires_grad`` pattern on every call, and -- under autocast -- ``cache_enabled=False`` for the step (``autocast_kwargs``).
 A call whose arguments do not match the captured signature runs the eager forward.
+
+In eval mode (``model.eval()`` before the call) the same parts are captured forward-only (plain ``torch.cuda.CUDAGraph`` with
+static input / output buffers): whole-model inference at batch 1 is launch-bound too.  The captured outputs live in static
+buffers that the next call overwrites -- upstream consumes them inside the same forward (the post-processor builds new tensors).
 """
 from __future__ import annotations
 
@@ -61,6 +65,28 @@ class _Signature:
             return False
         grad = torch.is_grad_enabled()
         return all((tens[n].shape, tens[n].dtype, tens[n].requires_grad and grad) == (m[0], m[1], m[2]) for n, m in zip(self.names, self.meta))
+
+
+class _ForwardGraph:
+    """Forward-only capture of ``fn(*tensors)`` (inference): static inputs, one graph, static outputs."""
+
+    def __init__(self, fn, sample_args: Sequence[Tensor], num_warmup_iters: int = 3):
+        self.static_in = [a.detach().clone() for a in sample_args]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(num_warmup_iters):
+                fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(*self.static_in)
+
+    def __call__(self, *args: Tensor):
+        for dst, src in zip(self.static_in, args):
+            dst.copy_(src)
+        self.graph.replay()
+        return self.static_out
 
 
 class GraphHandle:
@@ -111,8 +137,7 @@ def capture_static_parts(model: nn.Module, images, targets, autocast_dtype: Opti
                          parts: Sequence[str] = ("backbone", "encoder", "decoder"), num_warmup_iters: int = 3) -> GraphHandle:
     """Captures the listed parts of a reference ``RelationDETR`` in training mode for the input shapes of ``(images, targets)``.
     Call it BEFORE wrapping the model in DistributedDataParallel."""
-    if not model.training:
-        raise RuntimeError("capture_static_parts: put the model in training mode first (the graphs hold the backward too)")
+    training = model.training   # training: forward + backward graphs (make_graphed_callables); eval: forward-only graphs
     handle = GraphHandle()
 
     def ctx():
@@ -126,7 +151,11 @@ def capture_static_parts(model: nn.Module, images, targets, autocast_dtype: Opti
         modules["encoder"] = transformer.encoder
     if "decoder" in parts:
         modules["decoder"] = transformer.decoder
-    calls = _record_calls(model, modules, images, targets, ctx)
+    if training:
+        calls = _record_calls(model, modules, images, targets, ctx)
+    else:
+        with torch.no_grad():
+            calls = _record_calls(model, modules, images, None, ctx)
     torch.cuda.synchronize()
 
     with ctx():
@@ -134,10 +163,27 @@ def capture_static_parts(model: nn.Module, images, targets, autocast_dtype: Opti
             (x,), kw = calls["backbone"][0]
             if not kw and isinstance(x, Tensor):
                 bb = model.backbone
+                had_bb = "forward" in bb.__dict__
                 eager = bb.forward
-                torch.cuda.make_graphed_callables(bb, (x,), num_warmup_iters=num_warmup_iters)   # patches bb.forward in place
+                if training:
+                    torch.cuda.make_graphed_callables(bb, (x,), num_warmup_iters=num_warmup_iters)   # patches bb.forward in place
+                else:
+                    fg = _ForwardGraph(lambda t, bb=bb: type(bb).forward(bb, t), (x,), num_warmup_iters)
+                    sig = (x.shape, x.dtype)
+
+                    def bb_dispatch(t, bb=bb, fg=fg, sig=sig):
+                        if not bb.training and (t.shape, t.dtype) == sig and not torch.is_grad_enabled():
+                            return fg(t)
+                        return type(bb).forward(bb, t)
+                    bb.forward = bb_dispatch
                 handle.parts.append("backbone")
-                handle._undo.append(lambda bb=bb, eager=eager: setattr(bb, "forward", eager))
+
+                def undo_bb(bb=bb, had_bb=had_bb, eager=eager):
+                    if had_bb:
+                        bb.forward = eager
+                    else:
+                        bb.__dict__.pop("forward", None)
+                handle._undo.append(undo_bb)
         for name in ("encoder", "decoder"):
             if name not in modules:
                 continue
@@ -150,15 +196,18 @@ def capture_static_parts(model: nn.Module, images, targets, autocast_dtype: Opti
                 consts = {k: v for k, v in kw.items() if not isinstance(v, Tensor)}
                 tensors = [kw[k] for k in names]
                 wrapper = _Positional(inner, names, consts)
-                wrapper.train()
-                torch.cuda.make_graphed_callables(wrapper, tuple(tensors), num_warmup_iters=num_warmup_iters,
-                                                  allow_unused_input=True)
-                variants.append((_Signature(names, consts, tensors), wrapper))
+                wrapper.train(training)
+                if training:
+                    torch.cuda.make_graphed_callables(wrapper, tuple(tensors), num_warmup_iters=num_warmup_iters,
+                                                      allow_unused_input=True)
+                    variants.append((_Signature(names, consts, tensors), wrapper))
+                else:
+                    variants.append((_Signature(names, consts, tensors), _ForwardGraph(wrapper, tensors, num_warmup_iters)))
             if not variants:
                 continue
 
-            def dispatch(*args, _inner=inner, _variants=variants, **kwargs):
-                if not args and _inner.training:
+            def dispatch(*args, _inner=inner, _variants=variants, _training=training, **kwargs):
+                if not args and _inner.training == _training and (_training or not torch.is_grad_enabled()):
                     for sig, wrapper in _variants:
                         if sig.matches(kwargs):
                             return wrapper(*[kwargs[n] for n in sig.names])

@@ -69,3 +69,42 @@ def test_captured_parts_reproduce_the_eager_step(amp):
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
         rinstall.uninstall()
+
+
+@pytest.mark.parametrize("amp", [None, torch.bfloat16])
+def test_forward_only_capture_reproduces_eager_inference(amp):
+    """model.eval(): backbone, encoder and the decoder pass captured forward-only; detections must be those of the eager model,
+    for the captured image and for another image of the same size."""
+    refmodel.activate()
+    rinstall.uninstall()
+    rinstall.install()
+    torch.manual_seed(0)
+    model, _ = refmodel.build_relation_detr_r50(enc_layers=2, dec_layers=2)
+    rinstall.uninstall()
+    model.eval_transform = None
+    model = model.to(DEV).eval()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    img_a = torch.randn((3, 416, 544), device=DEV, generator=g)
+    img_b = torch.randn((3, 416, 544), device=DEV, generator=g)
+
+    def detect(img):
+        with torch.inference_mode(), torch.autocast("cuda", dtype=amp, enabled=amp is not None, cache_enabled=False):
+            det = model((img,))[0]
+        return {k: v.clone() for k, v in det.items()}
+
+    want_a, want_b = detect(img_a), detect(img_b)
+    handle = graphs.capture_static_parts(model, (img_a,), None, autocast_dtype=amp)
+    try:
+        assert handle.parts == ["backbone", "encoder x1", "decoder x1"], handle.parts
+        got_a, got_b, got_a2 = detect(img_a), detect(img_b), detect(img_a)
+    finally:
+        handle.release()
+    for got, want in ((got_a, want_a), (got_b, want_b), (got_a2, want_a)):
+        assert got.keys() == want.keys()
+        for k in want:
+            if want[k].is_floating_point():
+                assert (got[k].float() - want[k].float()).abs().max().item() <= 1e-4 * max(1.0, want[k].float().abs().max().item()), k
+            else:
+                assert torch.equal(got[k], want[k]), k
+    assert not (want_a["scores"] == want_b["scores"]).all()   # the two images do give different detections
+    assert "forward" not in model.backbone.__dict__ and "forward" not in model.transformer.decoder.__dict__
