@@ -229,3 +229,32 @@ def test_generators_are_deterministic_on_cpu():
     px = strict * wh[None, None, None, :, None, :] - 0.5
     frac = px - px.floor()
     assert ((frac > 0.004) & (frac < 0.996)).all()  # the strict generator keeps samples off pixel boundaries
+
+
+def test_graph_capture_helpers_host_logic():
+    """relation_detr_b200.graphs on the host: the positional wrapper forwards keyword arguments to the CLASS's forward (the
+    instance attribute is the dispatcher), the signature check tells calls apart, release() restores the instance."""
+    import torch
+    from torch import nn
+
+    from relation_detr_b200 import graphs
+
+    class Inner(nn.Module):
+        def forward(self, a, b=None, flag=False):
+            return a * 2 + (0 if b is None else b) + (1 if flag else 0)
+
+    inner = Inner()
+    inner.forward = lambda *a, **k: (_ for _ in ()).throw(AssertionError("the wrapper must bypass the instance attribute"))
+    w = graphs._Positional(inner, ["a", "b"], {"flag": True})
+    x, y = torch.ones(3), torch.full((3,), 5.0)
+    assert torch.equal(w(x, y), x * 2 + y + 1)
+    sig = graphs._Signature(["a", "b"], {"flag": True}, [x, y])
+    assert sig.matches({"a": x, "b": y, "flag": True})
+    assert not sig.matches({"a": x, "b": y, "flag": False})
+    assert not sig.matches({"a": x, "flag": True})
+    assert not sig.matches({"a": torch.ones(4), "b": y, "flag": True})
+    assert graphs.autocast_kwargs(torch.bfloat16)["cache_enabled"] is False
+    h = graphs.GraphHandle()
+    h._undo.append(lambda: inner.__dict__.pop("forward"))
+    h.release()
+    assert "forward" not in inner.__dict__ and torch.equal(inner(x), x * 2)
