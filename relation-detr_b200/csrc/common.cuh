@@ -73,6 +73,17 @@ __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float 
                  : "memory");
 }
 
+// base + off elements (off >= 0) as ONE instruction (IMAD.WIDE.U32); left to itself ptxas folds the lane's constant
+// offset into a 32-bit add and rebuilds the 64-bit address with four LEA / IADD3 per corner, and a signed offset
+// costs an IADD3 + LEA.HI.X.SX32 pair
+template <typename T>
+__device__ __forceinline__ T *elem_ptr(T *base, int off)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"((unsigned)off), "r"((unsigned)sizeof(T)), "l"((unsigned long long)base));
+    return reinterpret_cast<T *>(r);
+}
+
 // bf16 pair packed in a 32-bit word -> two floats (exact: bf16 is the top half of an fp32)
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }

@@ -39,7 +39,8 @@ template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
-                float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs)
+                float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs,
+                int red_levels)
 {
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
@@ -83,12 +84,23 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         float a;
         const Tap t = sample_tap(io, pair0, sw.s, pair, lp, l, LP, L, S, s_meta[pair * stride + lp].x, s_stat, s_bq, s_b, s_H, s_W,
                                  s_start, s_invW, s_invH, inv_P, a);
-        s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
+        const int ps = M * D;  // element offsets (S*M*D < 2^31, validate_msda): a corner's address is one multiply-add
+        s_pix[pair * stride + lp] = make_int4(t.pix[0] >= 0 ? t.pix[0] * ps : -1, t.pix[1] >= 0 ? t.pix[1] * ps : -1,
+                                              t.pix[2] >= 0 ? t.pix[2] * ps : -1, t.pix[3] >= 0 ? t.pix[3] * ps : -1);
         s_meta[pair * stride + lp] = make_float4(t.lw, t.lh, a, 0.f);
+    }
+    // pairs past the end (last CTA only): all corners invalid, so phase 2 needs no per-lane guard
+    for (int s = nsamples + threadIdx.x; s < kPairs * LP; s += kBwdThreads) {
+        s_pix[(s / LP) * stride + s % LP] = make_int4(-1, -1, -1, -1);
+        s_meta[(s / LP) * stride + s % LP] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
     // ---- phase 2 -----------------------------------------------------------------------------------
+    // Per corner i the lane forms d_i = <grad_out, value_i> over its channels; the bilinear algebra on top of the four
+    // d_i (cuh:110-141 of the reference: d/d(w_im), d/d(h_im), d/d(attn)) is linear in them, so it moves behind the
+    // cross-lane reduction and into phase 3, where one THREAD does it per sample instead of one WARP per four pairs.
+    // The four partials are reduced over the pair's 8 lanes by a transposing butterfly (4 shuffles instead of 9).
     const int pair = threadIdx.x / kLanes;
     const int lane = threadIdx.x - pair * kLanes;
     const bool active = pair < npairs;
@@ -98,7 +110,6 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     const long long batch_off = (b * S * M + m) * (long long)D + lane * kCh;
     const VT *vbase = value + batch_off;
     float *gvbase = grad_value_f32 + batch_off;
-    const int pix_stride = M * D;
 
     float g[kCh];
 #pragma unroll
@@ -107,56 +118,84 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     const int4 *my_pix = s_pix + pair * stride;
     float4 *my_meta = s_meta + pair * stride;
+    const bool odd1 = lane & 1, odd2 = lane & 2;
+    const int dot_slot = ((lane & 1) << 1) | ((lane >> 1) & 1);  // lanes 0..3 of the pair end up with d0, d2, d1, d3
+    for (int l = 0, lp = 0; l < L; ++l) {
+        const bool scatter = l < red_levels;  // levels >= red_levels: grad_value is accumulated by msda_bwd_coarse_kernel
 #pragma unroll 2
-    for (int lp = 0; lp < LP; ++lp) {
-        int4 px = make_int4(-1, -1, -1, -1);
-        float4 mt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            px = my_pix[lp];
-            mt = my_meta[lp];
-        }
-        const float lw = mt.x, lh = mt.y, a = mt.z;
-        const float hw = 1.f - lw, hh = 1.f - lh;
-        float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
+        for (int p = 0; p < P; ++p, ++lp) {
+            const int4 px = my_pix[lp];
+            const float4 mt = my_meta[lp];
+            const float lw = mt.x, lh = mt.y, a = mt.z;
+            const float hw = 1.f - lw, hh = 1.f - lh;
+            const float w0 = (hh * hw) * a, w1 = (hh * lw) * a, w2 = (lh * hw) * a, w3 = (lh * lw) * a;
+            float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
+            if (__all_sync(0xffffffffu, (px.x | px.y | px.z | px.w) >= 0)) {
+                SL::load(elem_ptr(vbase, px.x), v0);
+                SL::load(elem_ptr(vbase, px.y), v1);
+                SL::load(elem_ptr(vbase, px.z), v2);
+                SL::load(elem_ptr(vbase, px.w), v3);
+                if (scatter) {
 #pragma unroll
-        for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
-        if (px.x >= 0) SL::load(vbase + (long long)px.x * pix_stride, v0);
-        if (px.y >= 0) SL::load(vbase + (long long)px.y * pix_stride, v1);
-        if (px.z >= 0) SL::load(vbase + (long long)px.z * pix_stride, v2);
-        if (px.w >= 0) SL::load(vbase + (long long)px.w * pix_stride, v3);
-
-        const float w0 = hh * hw, w1 = hh * lw, w2 = lh * hw, w3 = lh * lw;
-        float p_attn = 0.f, p_gw = 0.f, p_gh = 0.f;
-        float tg[kCh];
+                    for (int c0 = 0; c0 < kCh; c0 += 4) {
+                        red_add_f32x4(elem_ptr(gvbase, px.x) + c0, w0 * g[c0], w0 * g[c0 + 1], w0 * g[c0 + 2], w0 * g[c0 + 3]);
+                        red_add_f32x4(elem_ptr(gvbase, px.y) + c0, w1 * g[c0], w1 * g[c0 + 1], w1 * g[c0 + 2], w1 * g[c0 + 3]);
+                        red_add_f32x4(elem_ptr(gvbase, px.z) + c0, w2 * g[c0], w2 * g[c0 + 1], w2 * g[c0 + 2], w2 * g[c0 + 3]);
+                        red_add_f32x4(elem_ptr(gvbase, px.w) + c0, w3 * g[c0], w3 * g[c0 + 1], w3 * g[c0 + 2], w3 * g[c0 + 3]);
+                    }
+                }
+            } else {
 #pragma unroll
-        for (int c = 0; c < kCh; ++c) {
-            tg[c] = g[c] * a;
-            const float bil = fmaf(w3, v3[c], fmaf(w2, v2[c], fmaf(w1, v1[c], w0 * v0[c])));
-            // d(bilinear)/d(w_im) and d/d(h_im), cuh:110-141 of the reference
-            const float dw = fmaf(hh, v1[c] - v0[c], lh * (v3[c] - v2[c]));
-            const float dh = fmaf(hw, v2[c] - v0[c], lw * (v3[c] - v1[c]));
-            p_attn = fmaf(g[c], bil, p_attn);
-            p_gw = fmaf(tg[c], dw, p_gw);
-            p_gh = fmaf(tg[c], dh, p_gh);
-        }
-        // grad_value scatter: one 16-byte vector reduction per lane and corner
+                for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
+                if (px.x >= 0) SL::load(elem_ptr(vbase, px.x), v0);
+                if (px.y >= 0) SL::load(elem_ptr(vbase, px.y), v1);
+                if (px.z >= 0) SL::load(elem_ptr(vbase, px.z), v2);
+                if (px.w >= 0) SL::load(elem_ptr(vbase, px.w), v3);
+                if (scatter) {
 #pragma unroll
-        for (int c0 = 0; c0 < kCh; c0 += 4) {
-            if (px.x >= 0) red_add_f32x4(gvbase + (long long)px.x * pix_stride + c0, w0 * tg[c0], w0 * tg[c0 + 1], w0 * tg[c0 + 2], w0 * tg[c0 + 3]);
-            if (px.y >= 0) red_add_f32x4(gvbase + (long long)px.y * pix_stride + c0, w1 * tg[c0], w1 * tg[c0 + 1], w1 * tg[c0 + 2], w1 * tg[c0 + 3]);
-            if (px.z >= 0) red_add_f32x4(gvbase + (long long)px.z * pix_stride + c0, w2 * tg[c0], w2 * tg[c0 + 1], w2 * tg[c0 + 2], w2 * tg[c0 + 3]);
-            if (px.w >= 0) red_add_f32x4(gvbase + (long long)px.w * pix_stride + c0, w3 * tg[c0], w3 * tg[c0 + 1], w3 * tg[c0 + 2], w3 * tg[c0 + 3]);
-        }
-        // combine the kLanes per-lane partials of this (b,q,m)
+                    for (int c0 = 0; c0 < kCh; c0 += 4) {
+                        if (px.x >= 0) red_add_f32x4(elem_ptr(gvbase, px.x) + c0, w0 * g[c0], w0 * g[c0 + 1], w0 * g[c0 + 2], w0 * g[c0 + 3]);
+                        if (px.y >= 0) red_add_f32x4(elem_ptr(gvbase, px.y) + c0, w1 * g[c0], w1 * g[c0 + 1], w1 * g[c0 + 2], w1 * g[c0 + 3]);
+                        if (px.z >= 0) red_add_f32x4(elem_ptr(gvbase, px.z) + c0, w2 * g[c0], w2 * g[c0 + 1], w2 * g[c0 + 2], w2 * g[c0 + 3]);
+                        if (px.w >= 0) red_add_f32x4(elem_ptr(gvbase, px.w) + c0, w3 * g[c0], w3 * g[c0 + 1], w3 * g[c0 + 2], w3 * g[c0 + 3]);
+                    }
+                }
+            }
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-        for (int off = kLanes / 2; off > 0; off >>= 1) {
-            p_attn += __shfl_xor_sync(0xffffffffu, p_attn, off);
-            p_gw += __shfl_xor_sync(0xffffffffu, p_gw, off);
-            p_gh += __shfl_xor_sync(0xffffffffu, p_gh, off);
+            for (int c = 0; c < kCh; ++c) {
+                d0 = fmaf(g[c], v0[c], d0);
+                d1 = fmaf(g[c], v1[c], d1);
+                d2 = fmaf(g[c], v2[c], d2);
+                d3 = fmaf(g[c], v3[c], d3);
+            }
+            // transposing butterfly over the pair's lanes: 4 values x 8 lanes -> every value summed, one per lane
+            static_assert(kLanes == 8, "the butterfly below is written for 8 lanes per pair");
+            float x = odd1 ? d2 : d0, y = odd1 ? d3 : d1;
+            x += __shfl_xor_sync(0xffffffffu, odd1 ? d0 : d2, 1);
+            y += __shfl_xor_sync(0xffffffffu, odd1 ? d1 : d3, 1);
+            float z = odd2 ? y : x;
+            z += __shfl_xor_sync(0xffffffffu, odd2 ? x : y, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 4);
+            // the pixel slot is dead after this iteration: it receives (d0, d1, d2, d3)
+            if (lane < 4) reinterpret_cast<float *>(const_cast<int4 *>(my_pix + lp))[dot_slot] = z;
         }
-        if (active && lane == 0) my_meta[lp] = make_float4(p_gw, p_gh, p_attn, a);  // .w keeps the attention weight
     }
     __syncthreads();
+
+    // (gw, gh, ga, a) of every sample from its four reduced dot products -- one thread per sample
+    for (SampleWalk sw(threadIdx.x, kBwdThreads, LP); sw.s < nsamples; sw.next(kBwdThreads)) {
+        const int idx = sw.pair * stride + sw.lp;
+        const float4 d = *reinterpret_cast<const float4 *>(s_pix + idx);
+        const float4 mt = s_meta[idx];
+        const float lw = mt.x, lh = mt.y, a = mt.z;
+        const float hw = 1.f - lw, hh = 1.f - lh;
+        const float ga = fmaf(lh * lw, d.w, fmaf(lh * hw, d.z, fmaf(hh * lw, d.y, (hh * hw) * d.x)));
+        const float gw = a * fmaf(hh, d.y - d.x, lh * (d.w - d.z));
+        const float gh = a * fmaf(hw, d.z - d.x, lw * (d.w - d.y));
+        s_meta[idx] = make_float4(gw, gh, ga, a);
+    }
+    if constexpr (IO::kFused) __syncthreads();  // the softmax backward below reads other threads' slots
 
     // ---- phase 3: dense stores of the per-sample gradients -------------------------------------------
     if constexpr (IO::kFused) {
@@ -233,10 +272,14 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
                                 "cudaFuncSetAttribute(msda_bwd)"))
             return rc;
     }
+    int red_levels = L;
+#ifdef RDETR_TUNE_FWD
+    if (const char *e = getenv("RDETR_MSDA_BWD_RED_LEVELS")) red_levels = atoi(e);  // timing experiments only (wrong grad_value)
+#endif
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
     kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
-                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs);
+                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs, red_levels);
     return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
 }
 
@@ -255,7 +298,8 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
     const int v = e ? atoi(e) : 0;
     if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
     if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
-    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 10>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    if (v == 4) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
 #endif
     // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls; register
     // caps for more occupancy spill and are 30-70 % slower (variant 3)

@@ -27,7 +27,12 @@ namespace rdetr {
 // L1 data pipe is 61 % busy), and with 64 threads the prologue / barrier of one CTA overlaps the gathers
 // of the others resident on the SM (tools/tune_fwd.py: 0.68 -> 0.61 ms at configs[1]; capping fp32 at 32
 // registers for full occupancy gives 0.57 ms).  MINB = 0 leaves the register budget to ptxas.
-template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
+// LEAN (default): phase 1 stages ELEMENT OFFSETS (pixel index * M*D) instead of pixel indices, so that a corner's
+// address is one IMAD.WIDE (the 64-bit multiply-add per corner was 5 instructions: 79 of the 225 of four samples),
+// and a warp whose four corners are all inside the level -- decided by one vote -- gathers without predicates
+// and without zero-filling the 16 landing registers (31 CS2R + 16 ISETP per four samples).  LEAN = false is the
+// round-1 loop, kept for tuning builds (tools/tune_fwd.py).
+template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0, bool LEAN = true>
 __global__ void __launch_bounds__(THREADS, MINB)
 msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, VT *__restrict__ out, int S, int M, int L, int Nq,
@@ -76,16 +81,31 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         const Tap t = sample_tap(io, pair0, sw.s, pair, lp, l, LP, L, S, s_wgt[pair * stride + lp].x, s_stat, s_bq, s_b, s_H, s_W,
                                  s_start, s_invW, s_invH, inv_P, a);
         const float hh = 1.f - t.lh, hw = 1.f - t.lw;
-        s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
+        if constexpr (LEAN) {
+            const int ps = M * D;  // S*M*D < 2^31 (validate_msda): the offsets fit an int
+            s_pix[pair * stride + lp] = make_int4(t.pix[0] >= 0 ? t.pix[0] * ps : -1, t.pix[1] >= 0 ? t.pix[1] * ps : -1,
+                                                  t.pix[2] >= 0 ? t.pix[2] * ps : -1, t.pix[3] >= 0 ? t.pix[3] * ps : -1);
+        } else {
+            s_pix[pair * stride + lp] = make_int4(t.pix[0], t.pix[1], t.pix[2], t.pix[3]);
+        }
         s_wgt[pair * stride + lp] = make_float4(a * (hh * hw), a * (hh * t.lw), a * (t.lh * hw), a * (t.lh * t.lw));
+    }
+    if constexpr (LEAN) {  // pairs past the end (last CTA only): all corners invalid, so phase 2 needs no per-lane guard
+        for (int s = nsamples + threadIdx.x; s < kPairs * LP; s += kFwdThreads) {
+            s_pix[(s / LP) * stride + s % LP] = make_int4(-1, -1, -1, -1);
+            s_wgt[(s / LP) * stride + s % LP] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     __syncthreads();
 
     // ---- phase 2: gather ---------------------------------------------------------------------------
     const int pair = threadIdx.x / kLanes;
     const int lane = threadIdx.x - pair * kLanes;
-    if (pair >= npairs) return;
-    const long long gp = pair0 + pair;
+    if constexpr (!LEAN) {
+        if (pair >= npairs) return;
+    }
+    const bool active = pair < npairs;
+    const long long gp = pair0 + (active ? pair : 0);
     const int m = (int)(gp % M);
     const long long b = (gp / M) / Nq;
     const VT *vbase = value + (b * S * M + m) * (long long)D + lane * kCh;
@@ -97,6 +117,35 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
 
     const int4 *my_pix = s_pix + pair * stride;
     const float4 *my_wgt = s_wgt + pair * stride;
+    if constexpr (LEAN) {
+#pragma unroll 4
+        for (int lp = 0; lp < LP; ++lp) {
+            const int4 px = my_pix[lp];
+            const float4 w = my_wgt[lp];
+            float v0[kCh], v1[kCh], v2[kCh], v3[kCh];
+            if (__all_sync(0xffffffffu, (px.x | px.y | px.z | px.w) >= 0)) {
+                SL::load(elem_ptr(vbase, px.x), v0);
+                SL::load(elem_ptr(vbase, px.y), v1);
+                SL::load(elem_ptr(vbase, px.z), v2);
+                SL::load(elem_ptr(vbase, px.w), v3);
+            } else {
+#pragma unroll
+                for (int c = 0; c < kCh; ++c) v0[c] = v1[c] = v2[c] = v3[c] = 0.f;
+                if (px.x >= 0) SL::load(elem_ptr(vbase, px.x), v0);
+                if (px.y >= 0) SL::load(elem_ptr(vbase, px.y), v1);
+                if (px.z >= 0) SL::load(elem_ptr(vbase, px.z), v2);
+                if (px.w >= 0) SL::load(elem_ptr(vbase, px.w), v3);
+            }
+#pragma unroll
+            for (int c = 0; c < kCh; ++c) {
+                acc[c] = fmaf(w.x, v0[c], acc[c]);
+                acc[c] = fmaf(w.y, v1[c], acc[c]);
+                acc[c] = fmaf(w.z, v2[c], acc[c]);
+                acc[c] = fmaf(w.w, v3[c], acc[c]);
+            }
+        }
+        if (!active) return;
+    } else {
 #pragma unroll 4
     for (int lp = 0; lp < LP; ++lp) {
         const int4 px = my_pix[lp];
@@ -116,6 +165,7 @@ msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
             acc[c] = fmaf(w.w, v3[c], acc[c]);
         }
     }
+    }
     SL::store(out + gp * D + lane * kCh, acc);
 }
 
@@ -126,7 +176,7 @@ template <typename VT, int CH, typename IO>
 int launch_fwd_tile(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B, int S, int M, int L,
                     int Nq, int P, cudaStream_t stream);
 
-template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
+template <typename VT, int CH, typename IO, int THREADS, int MINB = 0, bool LEAN = true>
 static int launch_fwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, void *out, int B,
                               int S, int M, int L, int Nq, int P, cudaStream_t stream)
 {
@@ -135,7 +185,7 @@ static int launch_fwd_variant(const void *value, const int64_t *shapes, const in
     constexpr int kPairs = THREADS / kLanes;
     const long long total_pairs = (long long)B * Nq * M;
     const size_t smem = (size_t)kPairs * (L * P + 1) * 32 + (IO::kFused ? kPairs * sizeof(float2) : 0);
-    auto kern = msda_fwd_kernel<VT, CH, D, IO, THREADS, MINB>;
+    auto kern = msda_fwd_kernel<VT, CH, D, IO, THREADS, MINB, LEAN>;
     if (smem > 48 * 1024) {
         if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                 "cudaFuncSetAttribute(msda_fwd)"))
@@ -169,15 +219,22 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
     if (v == 5) return launch_fwd_variant<VT, CH, IO, 64, 24>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 6) return launch_fwd_variant<VT, CH, IO, 128, 16>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 7) return launch_fwd_variant<VT, CH, IO, 32, 32>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 8) return launch_fwd_variant<VT, CH, IO, 64, sizeof(VT) == 4 ? 32 : 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 9) return launch_fwd_variant<VT, CH, IO, 64, 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 10) return launch_fwd_variant<VT, CH, IO, 64, 24>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if (v == 11) return launch_fwd_variant<VT, CH, IO, 128, 16>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
 #endif
-    // fp32: cap at 32 registers (32 CTAs x 2 warps = full occupancy; 0.62 -> 0.57 ms at configs[1]) as long as
-    // one image's value tensor fits L2 comfortably; for the 1200x2000 pyramid (209 MB per image) the extra
-    // CTAs in flight only widen the window of lines competing for L2 (0.90 ms uncapped vs 1.15 ms capped).
-    // The bf16 lanes hold 8 channels and spill under the cap, so they keep ptxas' own choice (71 registers).
+    // fp32: the round-1 loop capped at 32 registers (32 CTAs x 2 warps = full occupancy; 0.62 -> 0.57 ms at configs[1]) as
+    // long as one image's value tensor fits L2 comfortably; for the 1200x2000 pyramid (209 MB per image) the extra
+    // CTAs in flight only widen the window of lines competing for L2 (0.90 ms uncapped vs 1.15 ms capped).  The lean
+    // loop has a third fewer instructions per sample but does not fit 32 registers (spills: 0.99 ms) and at 42-48
+    // registers runs at 0.59-0.65 ms: the fp32 forward is bound by the L1 wavefront rate and by the warps in flight,
+    // not by issue slots (profiles/r02aa_exp_lean.txt).  bf16 lanes hold 8 channels (71 registers either way): there
+    // the lean loop wins (0.520 -> 0.493 ms; 1200x2000: 0.737 -> 0.684 ms).
     const bool fits_l2 = (size_t)S * M * 32 * sizeof(VT) <= (size_t)96 << 20;
     if (sizeof(VT) == 4 && fits_l2)
-        return launch_fwd_variant<VT, CH, IO, 64, sizeof(VT) == 4 ? 32 : 0>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
-    return launch_fwd_variant<VT, CH, IO, 64, 0>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        return launch_fwd_variant<VT, CH, IO, 64, sizeof(VT) == 4 ? 32 : 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    return launch_fwd_variant<VT, CH, IO, 64, 0, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
 }
 
 int validate_msda(const char *who, int B, int S, int M, int D, int L, int Nq, int P, int value_dtype)

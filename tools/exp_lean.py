@@ -1,0 +1,51 @@
+"""One-call experiment: parity of the lean MSDA kernels + timings of variants (tuning build).  Output: gpurun_out/r02aa_exp_lean.txt"""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+code = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+from relation_detr_b200 import ops, workloads
+shape = workloads.MSDA_SHAPES[os.environ.get("SHAPE", "msda_enc_800x1333_b8")]
+res = []
+def t(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+for kind in ("S", "U"):
+    inp = workloads.make_msda_inputs(shape, kind, seed=0, device="cuda:0")
+    for dt in (torch.float32, torch.bfloat16):
+        v = inp["value"].to(dt)
+        a = (v, inp["spatial_shapes"], inp["level_start_index"], inp["sampling_locations"], inp["attention_weights"])
+        f = t(lambda: ops.msda_forward(*a))
+        g = inp["grad_output"].to(dt)
+        b = t(lambda: ops.msda_backward(*a, g))
+        res.append("%%s/%%s fwd %%.4f bwd %%.4f" %% (kind, "f32" if dt == torch.float32 else "bf16", f, b))
+print(os.environ.get("TAG"), " | ".join(res))
+''' % ROOT
+lib = os.path.join(ROOT, "tools", "librdetr_tune.so")
+runs = [
+    ("default(lean)", {}),
+    ("fwd old capped (v8)", {"RDETR_MSDA_FWD_VARIANT": "8"}),
+    ("fwd lean uncapped 48reg (v4)", {"RDETR_MSDA_FWD_VARIANT": "4"}),
+    ("fwd lean 24 CTAs (v10)", {"RDETR_MSDA_FWD_VARIANT": "10"}),
+    ("fwd lean 128thr/16 (v11)", {"RDETR_MSDA_FWD_VARIANT": "11"}),
+    ("bwd 256 thr (v1)", {"RDETR_MSDA_BWD_VARIANT": "1"}),
+    ("bwd 64 thr (v2)", {"RDETR_MSDA_BWD_VARIANT": "2"}),
+    ("bwd 128 thr cap 10 CTAs (v3)", {"RDETR_MSDA_BWD_VARIANT": "3"}),
+    ("bwd 128 thr cap 12 CTAs (v4)", {"RDETR_MSDA_BWD_VARIANT": "4"}),
+    ("bwd reds only levels<3", {"RDETR_MSDA_BWD_RED_LEVELS": "3"}),
+    ("bwd reds only levels<2", {"RDETR_MSDA_BWD_RED_LEVELS": "2"}),
+    ("bwd reds only levels<1", {"RDETR_MSDA_BWD_RED_LEVELS": "1"}),
+    ("bwd no reds", {"RDETR_MSDA_BWD_RED_LEVELS": "0"}),
+    ("1200x2000 default", {"SHAPE": "msda_enc_1200x2000_b1"}),
+    ("1200x2000 fwd old uncapped (v9)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "9"}),
+    ("dec 900 default", {"SHAPE": "msda_dec_900_b8"}),
+]
+for tag, extra in runs:
+    env = dict(os.environ, RDETR_OPS_LIB=lib, TAG=tag, **extra)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:], flush=True)
