@@ -101,6 +101,17 @@ int rdetr_msda_backward(const void *value, const int64_t *spatial_shapes,
  */
 int rdetr_msda_set_tile_mode(int mode);
 int rdetr_msda_set_tile_rows(int rows);
+/*
+ * Backward only, experimental.  mode 2 (also RDETR_MSDA_COARSE=2 in the environment): pyramid levels of at most
+ * 1 056 pixels (25x42 and 13x21 of the 800x1333 pyramid, 19x32 of the 1200x2000 one) have their grad_value
+ * accumulated in shared memory by a second kernel on a library-owned high-priority side stream, next to the scatter
+ * kernel, instead of one L2 vector reduction per bilinear corner (csrc/msda_bwd_coarse.cu).  Which levels qualify is
+ * decided on the device from spatial_shapes.  The side stream forks from and joins the caller's stream with events
+ * inside the call (also under stream capture), so the call keeps its stream semantics.  Parity-tested
+ * (tests/test_msda_coarse_gpu.py) but SLOWER on B200, hence off by default: mode 0
+ * (default) and 1 = never, 2 = whenever P divides 8.  Results do not depend on the knob beyond fp32 summation order.
+ */
+int rdetr_msda_set_coarse_mode(int mode);
 
 /*
  * Multi-scale deformable attention with the module prologue folded in ("N2"):

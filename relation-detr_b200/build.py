@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "librdetr_ops.so")
-SOURCES = ["abi.cu", "msda_fwd.cu", "msda_fwd_tile.cu", "msda_bwd.cu", "msda_bwd_tile.cu", "rel.cu", "rel_attn.cu", "memfuse.cu", "topk.cu", "lsap.cu", "match_cost.cu", "diag.cu"]
+SOURCES = ["abi.cu", "msda_fwd.cu", "msda_fwd_tile.cu", "msda_bwd.cu", "msda_bwd_coarse.cu", "msda_bwd_tile.cu", "rel.cu", "rel_attn.cu", "memfuse.cu", "topk.cu", "lsap.cu", "match_cost.cu", "diag.cu"]
 
 
 def nvcc_path() -> str:

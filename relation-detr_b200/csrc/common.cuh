@@ -32,6 +32,11 @@ private:
 
 constexpr int kMaxLevels = 8;
 constexpr int kMaxPoints = 8;
+// msda_bwd_coarse.cu: a level with at most kCoarseCapRows pixels has its grad_value plane accumulated in shared
+// memory (128 B per row; 25x42 = 1 050 rows of the 800x1333 pyramid is the design point), one CTA per SM; planes of
+// at most kCoarseSmallRows (13x21 = 273) run several CTAs per SM.
+constexpr int kCoarseCapRows = 1056;
+constexpr int kCoarseSmallRows = 280;
 
 // ---- device side -------------------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -71,6 +76,22 @@ __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float 
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
+}
+
+__device__ __forceinline__ void red_add_f32x2(float *p, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// w * g[0..CH) added to row `p`: one vector reduction per lane
+template <int CH>
+__device__ __forceinline__ void red_row(float *p, float w, const float (&g)[CH])
+{
+    if constexpr (CH == 2) {
+        red_add_f32x2(p, w * g[0], w * g[1]);
+    } else {
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += 4) red_add_f32x4(p + c0, w * g[c0], w * g[c0 + 1], w * g[c0 + 2], w * g[c0 + 3]);
+    }
 }
 
 // base + off elements (off >= 0) as ONE instruction (IMAD.WIDE.U32); left to itself ptxas folds the lane's constant
@@ -129,6 +150,27 @@ struct Slice<float, 4> {
     __device__ __forceinline__ static void store(float *p, const float (&v)[4])
     {
         *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+// <float, 2>: 8-byte loads, 16 lanes per row -- a warp-wide load touches TWO 128-byte lines instead of four (tuning
+// variant of the forward: the L1 charges the lines of one instruction more than lines of separate instructions)
+template <>
+struct Slice<float, 2> {
+    static constexpr int kCh = 2;
+    __device__ __forceinline__ static void load(const float *p, float (&v)[2])
+    {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ static void load_stream(const float *p, float (&v)[2])
+    {
+        const float2 t = ld_stream_f2(reinterpret_cast<const float2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+    __device__ __forceinline__ static void store(float *p, const float (&v)[2])
+    {
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
     }
 };
 
@@ -193,6 +235,7 @@ struct Slice<__nv_bfloat16, 4> {
 struct Tap {
     int pix[4];
     float lw, lh;
+    int base;  // start + h0*W + w0 whether or not that corner exists (distance between the 2x2 footprints of two samples)
 };
 
 // `S` = rows of one image's value tensor: a corner whose pixel index reaches S (spatial_shapes / level_start_index
@@ -213,6 +256,7 @@ __device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int st
     const bool h0ok = inside && h0 >= 0, h1ok = inside && h1 <= H - 1;
     const bool w0ok = w0 >= 0, w1ok = w1 <= W - 1;
     const int base = start + h0 * W + w0;
+    t.base = base;
     t.pix[0] = (h0ok && w0ok) ? base : -1;
     t.pix[1] = (h0ok && w1ok) ? base + 1 : -1;
     t.pix[2] = (h1ok && w0ok) ? base + W : -1;
@@ -224,6 +268,15 @@ __device__ __forceinline__ Tap make_tap(float lx, float ly, int H, int W, int st
     }
     if (!inside) { t.lh = 0.f; t.lw = 0.f; }  // NaN / inf locations must not leak into weights
     return t;
+}
+
+// Levels whose whole (image, head) plane of grad_value fits a CTA's shared memory are accumulated there by
+// msda_bwd_coarse_kernel instead of going to L2 one vector reduction per corner; the scatter kernel and the coarse
+// kernel both decide with this predicate, from the shape tensors on the device.  `cap_rows` = 0 disables it.
+__device__ __forceinline__ bool coarse_level(int H, int W, int start, int S, int cap_rows)
+{
+    const long long rows = (long long)H * W;
+    return cap_rows > 0 && H > 0 && W > 0 && rows <= cap_rows && start >= 0 && start + rows <= S;
 }
 
 // Walks the sample ids s = tid, tid + T, tid + 2T, ... of a CTA and keeps (pair, lp) = (s / LP, s % LP) up to

@@ -35,12 +35,19 @@ template <typename VT, typename IO>
 int launch_bwd_tile(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out, float *gv_f32,
                     int B, int S, int M, int L, int Nq, int P, cudaStream_t stream);
 
+// msda_bwd_coarse.cu: grad_value of the levels that fit shared memory, on a side stream next to the scatter kernel
+int msda_coarse_cap_rows(int Nq, int P);
+template <typename VT, typename IO>
+int fork_coarse(const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out, float *gv_f32, int B, int S, int M,
+                int L, int Nq, int P, cudaStream_t main, cudaStream_t *side_out, cudaEvent_t *done_out);
+int join_coarse(cudaStream_t main, cudaEvent_t done);
+
 template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
                 float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs,
-                int red_levels)
+                int coarse_cap_rows)
 {
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
@@ -52,6 +59,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
     __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
     __shared__ unsigned char s_lvl[kMaxLevels * kMaxPoints];  // level of sample slot lp (= lp / P)
+    __shared__ unsigned char s_scatter[kMaxLevels];           // 0: the level's grad_value is accumulated by msda_bwd_coarse_kernel
     __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
     __shared__ int s_b[THREADS / (D / CH)];
     const float inv_P = 1.0f / (float)P;
@@ -67,6 +75,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
         s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
         s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
+        s_scatter[threadIdx.x] = !coarse_level(s_H[threadIdx.x], s_W[threadIdx.x], s_start[threadIdx.x], S, coarse_cap_rows);
     }
     for (int i = threadIdx.x; i < L * P; i += THREADS) s_lvl[i] = (unsigned char)(i / P);
     __syncthreads();
@@ -121,7 +130,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     const bool odd1 = lane & 1, odd2 = lane & 2;
     const int dot_slot = ((lane & 1) << 1) | ((lane >> 1) & 1);  // lanes 0..3 of the pair end up with d0, d2, d1, d3
     for (int l = 0, lp = 0; l < L; ++l) {
-        const bool scatter = l < red_levels;  // levels >= red_levels: grad_value is accumulated by msda_bwd_coarse_kernel
+        const bool scatter = s_scatter[l] != 0;  // else: grad_value of this level comes from msda_bwd_coarse_kernel
 #pragma unroll 2
         for (int p = 0; p < P; ++p, ++lp) {
             const int4 px = my_pix[lp];
@@ -136,13 +145,10 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 SL::load(elem_ptr(vbase, px.z), v2);
                 SL::load(elem_ptr(vbase, px.w), v3);
                 if (scatter) {
-#pragma unroll
-                    for (int c0 = 0; c0 < kCh; c0 += 4) {
-                        red_add_f32x4(elem_ptr(gvbase, px.x) + c0, w0 * g[c0], w0 * g[c0 + 1], w0 * g[c0 + 2], w0 * g[c0 + 3]);
-                        red_add_f32x4(elem_ptr(gvbase, px.y) + c0, w1 * g[c0], w1 * g[c0 + 1], w1 * g[c0 + 2], w1 * g[c0 + 3]);
-                        red_add_f32x4(elem_ptr(gvbase, px.z) + c0, w2 * g[c0], w2 * g[c0 + 1], w2 * g[c0 + 2], w2 * g[c0 + 3]);
-                        red_add_f32x4(elem_ptr(gvbase, px.w) + c0, w3 * g[c0], w3 * g[c0 + 1], w3 * g[c0 + 2], w3 * g[c0 + 3]);
-                    }
+                    red_row<kCh>(elem_ptr(gvbase, px.x), w0, g);
+                    red_row<kCh>(elem_ptr(gvbase, px.y), w1, g);
+                    red_row<kCh>(elem_ptr(gvbase, px.z), w2, g);
+                    red_row<kCh>(elem_ptr(gvbase, px.w), w3, g);
                 }
             } else {
 #pragma unroll
@@ -152,13 +158,10 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 if (px.z >= 0) SL::load(elem_ptr(vbase, px.z), v2);
                 if (px.w >= 0) SL::load(elem_ptr(vbase, px.w), v3);
                 if (scatter) {
-#pragma unroll
-                    for (int c0 = 0; c0 < kCh; c0 += 4) {
-                        if (px.x >= 0) red_add_f32x4(elem_ptr(gvbase, px.x) + c0, w0 * g[c0], w0 * g[c0 + 1], w0 * g[c0 + 2], w0 * g[c0 + 3]);
-                        if (px.y >= 0) red_add_f32x4(elem_ptr(gvbase, px.y) + c0, w1 * g[c0], w1 * g[c0 + 1], w1 * g[c0 + 2], w1 * g[c0 + 3]);
-                        if (px.z >= 0) red_add_f32x4(elem_ptr(gvbase, px.z) + c0, w2 * g[c0], w2 * g[c0 + 1], w2 * g[c0 + 2], w2 * g[c0 + 3]);
-                        if (px.w >= 0) red_add_f32x4(elem_ptr(gvbase, px.w) + c0, w3 * g[c0], w3 * g[c0 + 1], w3 * g[c0 + 2], w3 * g[c0 + 3]);
-                    }
+                    if (px.x >= 0) red_row<kCh>(elem_ptr(gvbase, px.x), w0, g);
+                    if (px.y >= 0) red_row<kCh>(elem_ptr(gvbase, px.y), w1, g);
+                    if (px.z >= 0) red_row<kCh>(elem_ptr(gvbase, px.z), w2, g);
+                    if (px.w >= 0) red_row<kCh>(elem_ptr(gvbase, px.w), w3, g);
                 }
             }
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
@@ -170,13 +173,14 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 d3 = fmaf(g[c], v3[c], d3);
             }
             // transposing butterfly over the pair's lanes: 4 values x 8 lanes -> every value summed, one per lane
-            static_assert(kLanes == 8, "the butterfly below is written for 8 lanes per pair");
+            static_assert(kLanes == 8 || kLanes == 16, "the butterfly below is written for 8 or 16 lanes per pair");
             float x = odd1 ? d2 : d0, y = odd1 ? d3 : d1;
             x += __shfl_xor_sync(0xffffffffu, odd1 ? d0 : d2, 1);
             y += __shfl_xor_sync(0xffffffffu, odd1 ? d1 : d3, 1);
             float z = odd2 ? y : x;
             z += __shfl_xor_sync(0xffffffffu, odd2 ? x : y, 2);
             z += __shfl_xor_sync(0xffffffffu, z, 4);
+            if constexpr (kLanes == 16) z += __shfl_xor_sync(0xffffffffu, z, 8);
             // the pixel slot is dead after this iteration: it receives (d0, d1, d2, d3)
             if (lane < 4) reinterpret_cast<float *>(const_cast<int4 *>(my_pix + lp))[dot_slot] = z;
         }
@@ -243,6 +247,18 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     }
 }
 
+__global__ void spin_kernel(long long ns)
+{
+    long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    for (;;) {
+        long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if (t - t0 >= ns) break;
+        __nanosleep(200);
+    }
+}
+
 // fp32 accumulation buffer -> bf16 grad_value (8 elements per thread)
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
                                                           long long n8)
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
 
 template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
 static int launch_bwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
-                              float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
+                              float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
@@ -272,20 +288,26 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
                                 "cudaFuncSetAttribute(msda_bwd)"))
             return rc;
     }
-    int red_levels = L;
 #ifdef RDETR_TUNE_FWD
-    if (const char *e = getenv("RDETR_MSDA_BWD_RED_LEVELS")) red_levels = atoi(e);  // timing experiments only (wrong grad_value)
+    if (const char *e = getenv("RDETR_MSDA_BWD_SKIP_ROWS")) coarse_cap = atoi(e);  // timing experiments only (levels of at most that many pixels get NO grad_value)
 #endif
+    // next to the coarse kernel (which needs the largest shared-memory carve-out) the scatter kernel asks for the same
+    // L1 / shared split: an SM cannot hold CTAs of two kernels that want different splits
+    static const int exp_carve = getenv("RDETR_COARSE_CARVEOUT") ? atoi(getenv("RDETR_COARSE_CARVEOUT")) : 1;
+    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 (coarse_cap > 0 && exp_carve) ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault),
+                            "cudaFuncSetAttribute(msda_bwd carveout)"))
+        return rc;
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
     kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
-                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs, red_levels);
+                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs, coarse_cap);
     return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
 }
 
 template <typename VT, int CH, typename IO>
 static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
-                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, cudaStream_t stream)
+                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, cudaStream_t stream)
 {
     // encoder self-attention (every query is a pixel of the pyramid): tiled kernel with shared-memory grad_value
     // accumulators (msda_bwd_tile.cu); rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
@@ -296,14 +318,19 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
 #ifdef RDETR_TUNE_FWD
     const char *e = getenv("RDETR_MSDA_BWD_VARIANT");
     const int v = e ? atoi(e) : 0;
-    if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
-    if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
-    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 10>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
-    if (v == 4) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 10>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    if constexpr (sizeof(VT) == 4) {
+        if (v == 5) return launch_bwd_variant<VT, 2, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+        if (v == 6) return launch_bwd_variant<VT, 2, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+        if (v == 7) return launch_bwd_variant<VT, 2, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    }
+    if (v == 4) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
 #endif
     // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls; register
     // caps for more occupancy spill and are 30-70 % slower (variant 3)
-    return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, stream);
+    return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
 }
 
 // zero-fill of the fp32 accumulation target, the scatter kernel, and (bf16) the final conversion
@@ -316,9 +343,28 @@ static int run_backward(const void *value, const int64_t *shapes, const int64_t 
     float *acc = dtype == RDETR_DTYPE_F32 ? static_cast<float *>(grad_value) : static_cast<float *>(workspace);
     if (int rc = check_cuda(cudaMemsetAsync(acc, 0, nvalue * sizeof(float), st), "cudaMemsetAsync(grad_value)")) return rc;
     if (Nq > 0) {
-        const int rc = dtype == RDETR_DTYPE_F32
-                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, st)
-                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, st);
+        // coarse levels: shared-memory accumulation on a side stream, concurrent with the scatter kernel (msda_bwd_coarse.cu)
+        const int cap = (Nq == S && msda_tile_mode() == 2) ? 0 : msda_coarse_cap_rows(Nq, P);
+        cudaStream_t side = nullptr;
+        cudaEvent_t done = nullptr;
+        if (cap > 0) {
+            const int rc = dtype == RDETR_DTYPE_F32
+                               ? fork_coarse<float>(shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, st, &side, &done)
+                               : fork_coarse<__nv_bfloat16>(shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, st, &side, &done);
+            if (rc) return rc;
+        }
+        int rc = RDETR_OK;
+        static const int exp_delay_us = getenv("RDETR_COARSE_DELAY_US") ? atoi(getenv("RDETR_COARSE_DELAY_US")) : 0;  // experiments
+        static const int exp_skip_scatter = getenv("RDETR_COARSE_ONLY") ? atoi(getenv("RDETR_COARSE_ONLY")) : 0;
+        if (cap > 0 && exp_delay_us > 0) spin_kernel<<<1, 32, 0, st>>>(exp_delay_us * 1000LL);
+        if (!(cap > 0 && exp_skip_scatter))
+        rc = dtype == RDETR_DTYPE_F32
+                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, cap, st)
+                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, cap, st);
+        if (cap > 0) {
+            const int rj = join_coarse(st, done);
+            if (rc == RDETR_OK && rj) return rj;
+        }
         if (rc) return rc;
     }
     if (dtype == RDETR_DTYPE_BF16) {

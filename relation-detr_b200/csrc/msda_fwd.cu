@@ -221,6 +221,12 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
     if (v == 7) return launch_fwd_variant<VT, CH, IO, 32, 32>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 8) return launch_fwd_variant<VT, CH, IO, 64, sizeof(VT) == 4 ? 32 : 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 9) return launch_fwd_variant<VT, CH, IO, 64, 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    if constexpr (sizeof(VT) == 4) {
+        if (v == 12) return launch_fwd_variant<VT, 2, IO, 64, 32, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 13) return launch_fwd_variant<VT, 2, IO, 64, 32, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 14) return launch_fwd_variant<VT, 2, IO, 128, 16, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 15) return launch_fwd_variant<VT, 2, IO, 64, 0, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+    }
     if (v == 10) return launch_fwd_variant<VT, CH, IO, 64, 24>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 11) return launch_fwd_variant<VT, CH, IO, 128, 16>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
 #endif

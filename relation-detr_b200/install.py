@@ -100,15 +100,20 @@ def install(reference_root: str | None = None, strict: bool = True, matcher_too:
         setattr(mod, attr, repl)
         report.append(key)
 
+    # Import every user BEFORE rebinding anything: `relation_transformer` does `from models.bricks.ms_deform_attn import
+    # MultiScaleDeformableAttention` at import time, so importing it after `ms_deform_attn` has been rebound would make
+    # this package's class look like the reference's own one -- uninstall() would then "restore" ours (found by the
+    # leak guard in tests/conftest.py when install() happened to be the first importer of the reference).
+    users = []
     for name in _MSDA_USERS:
         try:
-            mod = importlib.import_module(name)
+            users.append((name, importlib.import_module(name)))
         except Exception as e:
             if strict:
                 raise RuntimeError(f"relation_detr_b200.install: cannot import the reference module {name!r} "
                                    f"({type(e).__name__}: {e}); nothing of it was rebound") from e
             report.skipped.append(f"{name} ({type(e).__name__}: {e})")
-            continue
+    for name, mod in users:
         for attr, repl in (("MultiScaleDeformableAttention", modules.MultiScaleDeformableAttention),
                            ("MultiScaleDeformableAttnFunction", ops.MultiScaleDeformableAttnFunction),
                            ("PositionRelationEmbedding", modules.PositionRelationEmbedding)):

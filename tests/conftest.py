@@ -65,3 +65,21 @@ def relmax(a, ref):
     ref = np.asarray(ref, dtype=np.float64)
     den = float(np.max(np.abs(ref))) if ref.size else 1.0
     return maxabs(a, ref) / max(den, 1e-30)
+
+
+@pytest.fixture(autouse=True)
+def _no_leaked_install():
+    """No test may leave the reference's modules rebound to this package's classes behind its back: after every test,
+    either ``install._saved`` still knows how to undo the rebinding or nothing is rebound (an order-dependent failure
+    of the integration tests was traced with this guard)."""
+    yield
+    rt = sys.modules.get("models.bricks.relation_transformer")
+    if rt is None or "relation_detr_b200" not in sys.modules:
+        return
+    from relation_detr_b200 import install as rinstall
+    from relation_detr_b200 import modules
+    for attr in ("MultiScaleDeformableAttention", "PositionRelationEmbedding"):
+        ours = getattr(modules, attr)
+        if getattr(rt, attr, None) is ours:
+            assert f"models.bricks.relation_transformer.{attr}" in rinstall._saved, \
+                f"{attr} of the reference is rebound to relation_detr_b200's and install._saved has forgotten the original"

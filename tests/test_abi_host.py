@@ -258,3 +258,32 @@ def test_graph_capture_helpers_host_logic():
     h._undo.append(lambda: inner.__dict__.pop("forward"))
     h.release()
     assert "forward" not in inner.__dict__ and torch.equal(inner(x), x * 2)
+
+
+def test_install_as_first_importer_of_the_reference_is_undone_by_uninstall():
+    """install() in a fresh interpreter, where it is the first to import the reference's modules: relation_transformer
+    binds MultiScaleDeformableAttention from ms_deform_attn at import time, so every user must be imported before the
+    first name is rebound, or uninstall() restores this package's class as "the original" (order-dependent failure of
+    the GPU integration tests)."""
+    from baseline import refmodel
+    if not refmodel.available():
+        pytest.skip("baseline/_ref not installed")
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from baseline import refmodel\n"
+        "from relation_detr_b200 import install, modules\n"
+        "refmodel.activate()\n"
+        "assert 'models.bricks.relation_transformer' not in sys.modules\n"
+        "install.install()\n"
+        "rt = sys.modules['models.bricks.relation_transformer']\n"
+        "assert rt.MultiScaleDeformableAttention is modules.MultiScaleDeformableAttention\n"
+        "install.uninstall()\n"
+        "assert rt.MultiScaleDeformableAttention.__module__ == 'models.bricks.ms_deform_attn', rt.MultiScaleDeformableAttention\n"
+        "assert rt.PositionRelationEmbedding.__module__ == 'models.bricks.relation_transformer'\n"
+        "assert not install._saved\n"
+        "print('ok')\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -28,22 +28,18 @@ print(os.environ.get("TAG"), " | ".join(res))
 ''' % ROOT
 lib = os.path.join(ROOT, "tools", "librdetr_tune.so")
 runs = [
-    ("default(lean)", {}),
-    ("fwd old capped (v8)", {"RDETR_MSDA_FWD_VARIANT": "8"}),
-    ("fwd lean uncapped 48reg (v4)", {"RDETR_MSDA_FWD_VARIANT": "4"}),
-    ("fwd lean 24 CTAs (v10)", {"RDETR_MSDA_FWD_VARIANT": "10"}),
-    ("fwd lean 128thr/16 (v11)", {"RDETR_MSDA_FWD_VARIANT": "11"}),
-    ("bwd 256 thr (v1)", {"RDETR_MSDA_BWD_VARIANT": "1"}),
-    ("bwd 64 thr (v2)", {"RDETR_MSDA_BWD_VARIANT": "2"}),
-    ("bwd 128 thr cap 10 CTAs (v3)", {"RDETR_MSDA_BWD_VARIANT": "3"}),
-    ("bwd 128 thr cap 12 CTAs (v4)", {"RDETR_MSDA_BWD_VARIANT": "4"}),
-    ("bwd reds only levels<3", {"RDETR_MSDA_BWD_RED_LEVELS": "3"}),
-    ("bwd reds only levels<2", {"RDETR_MSDA_BWD_RED_LEVELS": "2"}),
-    ("bwd reds only levels<1", {"RDETR_MSDA_BWD_RED_LEVELS": "1"}),
-    ("bwd no reds", {"RDETR_MSDA_BWD_RED_LEVELS": "0"}),
-    ("1200x2000 default", {"SHAPE": "msda_enc_1200x2000_b1"}),
-    ("1200x2000 fwd old uncapped (v9)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "9"}),
-    ("dec 900 default", {"SHAPE": "msda_dec_900_b8"}),
+    ("default", {}),
+    ("fwd 2ch old loop cap32 (v12)", {"RDETR_MSDA_FWD_VARIANT": "12"}),
+    ("fwd 2ch lean cap32 (v13)", {"RDETR_MSDA_FWD_VARIANT": "13"}),
+    ("fwd 2ch lean 128thr/16 (v14)", {"RDETR_MSDA_FWD_VARIANT": "14"}),
+    ("fwd 2ch lean uncapped (v15)", {"RDETR_MSDA_FWD_VARIANT": "15"}),
+    ("bwd 2ch 128thr (v5)", {"RDETR_MSDA_BWD_VARIANT": "5"}),
+    ("bwd 2ch 256thr (v6)", {"RDETR_MSDA_BWD_VARIANT": "6"}),
+    ("bwd 2ch 128thr cap12 (v7)", {"RDETR_MSDA_BWD_VARIANT": "7"}),
+    ("1200x2000 fwd 2ch lean cap32 (v13)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "13"}),
+    ("1200x2000 fwd 2ch lean uncapped (v15)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "15"}),
+    ("1200x2000 bwd 2ch (v5)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_BWD_VARIANT": "5"}),
+    ("dec 900 fwd 2ch (v13) bwd 2ch (v5)", {"SHAPE": "msda_dec_900_b8", "RDETR_MSDA_FWD_VARIANT": "13", "RDETR_MSDA_BWD_VARIANT": "5"}),
 ]
 for tag, extra in runs:
     env = dict(os.environ, RDETR_OPS_LIB=lib, TAG=tag, **extra)
