@@ -174,6 +174,25 @@ struct Slice<float, 2> {
     }
 };
 
+// <float, 8>: 32-byte loads (LDG.E.256, sm_100), 4 lanes per row -- a warp-wide load gathers EIGHT 128-byte rows.  The LSU
+// accepts about one warp-level load per 7 cycles and SM whatever its width (profiles/r01_microbench.txt: 39 / 79 / 170 G
+// rows/s at 1 / 2 / 4 rows per instruction), so rows per instruction is the lever the fp32 forward had left.
+template <>
+struct Slice<float, 8> {
+    static constexpr int kCh = 8;
+    __device__ __forceinline__ static void load(const float *p, float (&v)[8])
+    {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    }
+    __device__ __forceinline__ static void store(float *p, const float (&v)[8])
+    {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
 template <>
 struct Slice<__nv_bfloat16, 8> {
     static constexpr int kCh = 8;

@@ -20,6 +20,7 @@
 // grad_value accumulates in fp32.  For bf16 value the accumulation target is an fp32 workspace that
 // a second kernel converts (bf16 accumulation would lose the small addends on coarse levels, where
 // one address receives ~1e3 updates).
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -292,12 +293,18 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
     if (const char *e = getenv("RDETR_MSDA_BWD_SKIP_ROWS")) coarse_cap = atoi(e);  // timing experiments only (levels of at most that many pixels get NO grad_value)
 #endif
     // next to the coarse kernel (which needs the largest shared-memory carve-out) the scatter kernel asks for the same
-    // L1 / shared split: an SM cannot hold CTAs of two kernels that want different splits
-    static const int exp_carve = getenv("RDETR_COARSE_CARVEOUT") ? atoi(getenv("RDETR_COARSE_CARVEOUT")) : 1;
-    if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                 (coarse_cap > 0 && exp_carve) ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault),
-                            "cudaFuncSetAttribute(msda_bwd carveout)"))
-        return rc;
+    // L1 / shared split: an SM does not hold CTAs of two kernels that want different splits.  Set only when it changes.
+    {
+        static const int exp_carve = getenv("RDETR_COARSE_CARVEOUT") ? atoi(getenv("RDETR_COARSE_CARVEOUT")) : 1;
+        static std::atomic<int> current{(int)cudaSharedmemCarveoutDefault};  // per instantiation of this template
+        const int want = (coarse_cap > 0 && exp_carve) ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
+        if (current.load(std::memory_order_relaxed) != want) {
+            if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want),
+                                    "cudaFuncSetAttribute(msda_bwd carveout)"))
+                return rc;
+            current.store(want, std::memory_order_relaxed);
+        }
+    }
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
     kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,

@@ -226,6 +226,11 @@ static int launch_fwd(const void *value, const int64_t *shapes, const int64_t *l
         if (v == 13) return launch_fwd_variant<VT, 2, IO, 64, 32, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
         if (v == 14) return launch_fwd_variant<VT, 2, IO, 128, 16, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
         if (v == 15) return launch_fwd_variant<VT, 2, IO, 64, 0, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 16) return launch_fwd_variant<VT, 8, IO, 64, 0, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 17) return launch_fwd_variant<VT, 8, IO, 64, 16, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 18) return launch_fwd_variant<VT, 8, IO, 64, 0, false>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 19) return launch_fwd_variant<VT, 8, IO, 128, 8, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
+        if (v == 20) return launch_fwd_variant<VT, 8, IO, 32, 0, true>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     }
     if (v == 10) return launch_fwd_variant<VT, CH, IO, 64, 24>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);
     if (v == 11) return launch_fwd_variant<VT, CH, IO, 128, 16>(value, shapes, lsi, io, out, B, S, M, L, Nq, P, stream);

@@ -29,17 +29,17 @@ print(os.environ.get("TAG"), " | ".join(res))
 lib = os.path.join(ROOT, "tools", "librdetr_tune.so")
 runs = [
     ("default", {}),
-    ("fwd 2ch old loop cap32 (v12)", {"RDETR_MSDA_FWD_VARIANT": "12"}),
-    ("fwd 2ch lean cap32 (v13)", {"RDETR_MSDA_FWD_VARIANT": "13"}),
-    ("fwd 2ch lean 128thr/16 (v14)", {"RDETR_MSDA_FWD_VARIANT": "14"}),
-    ("fwd 2ch lean uncapped (v15)", {"RDETR_MSDA_FWD_VARIANT": "15"}),
-    ("bwd 2ch 128thr (v5)", {"RDETR_MSDA_BWD_VARIANT": "5"}),
-    ("bwd 2ch 256thr (v6)", {"RDETR_MSDA_BWD_VARIANT": "6"}),
-    ("bwd 2ch 128thr cap12 (v7)", {"RDETR_MSDA_BWD_VARIANT": "7"}),
-    ("1200x2000 fwd 2ch lean cap32 (v13)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "13"}),
-    ("1200x2000 fwd 2ch lean uncapped (v15)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "15"}),
-    ("1200x2000 bwd 2ch (v5)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_BWD_VARIANT": "5"}),
-    ("dec 900 fwd 2ch (v13) bwd 2ch (v5)", {"SHAPE": "msda_dec_900_b8", "RDETR_MSDA_FWD_VARIANT": "13", "RDETR_MSDA_BWD_VARIANT": "5"}),
+    ("fwd 8ch LDG.256 lean uncapped (v16)", {"RDETR_MSDA_FWD_VARIANT": "16"}),
+    ("fwd 8ch LDG.256 lean 64thr/16 (v17)", {"RDETR_MSDA_FWD_VARIANT": "17"}),
+    ("fwd 8ch LDG.256 old loop (v18)", {"RDETR_MSDA_FWD_VARIANT": "18"}),
+    ("fwd 8ch LDG.256 lean 128thr/8 (v19)", {"RDETR_MSDA_FWD_VARIANT": "19"}),
+    ("fwd 8ch LDG.256 lean 32thr (v20)", {"RDETR_MSDA_FWD_VARIANT": "20"}),
+    ("1200x2000 default", {"SHAPE": "msda_enc_1200x2000_b1"}),
+    ("1200x2000 fwd 8ch LDG.256 (v16)", {"SHAPE": "msda_enc_1200x2000_b1", "RDETR_MSDA_FWD_VARIANT": "16"}),
+    ("dec 900 default", {"SHAPE": "msda_dec_900_b8"}),
+    ("dec 900 fwd 8ch LDG.256 (v16)", {"SHAPE": "msda_dec_900_b8", "RDETR_MSDA_FWD_VARIANT": "16"}),
+    ("enc b2 default", {"SHAPE": "msda_enc_800x1333_b2"}),
+    ("enc b2 fwd 8ch LDG.256 (v16)", {"SHAPE": "msda_enc_800x1333_b2", "RDETR_MSDA_FWD_VARIANT": "16"}),
 ]
 for tag, extra in runs:
     env = dict(os.environ, RDETR_OPS_LIB=lib, TAG=tag, **extra)
