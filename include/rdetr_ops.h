@@ -112,6 +112,19 @@ int rdetr_msda_set_tile_rows(int rows);
  * (default) and 1 = never, 2 = whenever P divides 8.  Results do not depend on the knob beyond fp32 summation order.
  */
 int rdetr_msda_set_coarse_mode(int mode);
+/*
+ * Backward with bf16 value only.  A pyramid level whose grad_value rows receive at most `max_updates_per_row` updates
+ * on average (Nq * P * 4 bilinear corners over H * W rows: 21 for the finest level of both shipped pyramids when
+ * Nq = S, 85 for the next) is scattered straight into the bf16 grad_value with packed bf16x2 vector reductions
+ * (64 bytes per row: 81 G rows/s at the L2 against 48 G rows/s for 128-byte fp32 rows, profiles/r02al_microbench_red.txt)
+ * instead of into the fp32 workspace; the other levels keep fp32 accumulation (a coarse row receives ~1e3 updates, which
+ * bf16 accumulation would swallow).  Every addition then rounds to bf16: the directly scattered rows carry about
+ * sqrt(updates) * 2^-9 relative error instead of the final rounding's 2^-9 (tests/test_msda_bf16_scatter_gpu.py bounds it
+ * level by level).  Default 100: the two finest levels of an encoder call, bf16 backward 1.91 -> 1.57 ms at configs[1]
+ * (profiles/r02am_exp_bf16_scatter.txt); 0 = never (also RDETR_MSDA_BF16_SCATTER in the environment).  Process-wide,
+ * safe to call from any thread.  fp32 calls are unaffected.
+ */
+int rdetr_msda_set_bf16_scatter(int max_updates_per_row);
 
 /*
  * Multi-scale deformable attention with the module prologue folded in ("N2"):

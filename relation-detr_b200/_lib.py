@@ -25,6 +25,7 @@ _SIGNATURES = {
     "rdetr_msda_backward": (c_int, [c_void_p] * 9 + [c_int] * 8 + [c_void_p, c_size_t, c_void_p]),
     "rdetr_msda_set_tile_mode": (c_int, [c_int]),
     "rdetr_msda_set_coarse_mode": (c_int, [c_int]),
+    "rdetr_msda_set_bf16_scatter": (c_int, [c_int]),
     "rdetr_msda_set_tile_rows": (c_int, [c_int]),
     "rdetr_msda_fused_forward": (c_int, [c_void_p] * 8 + [c_int] * 9 + [c_void_p]),
     "rdetr_msda_fused_backward": (c_int, [c_void_p] * 11 + [c_int] * 9 + [c_void_p, c_size_t, c_void_p]),

@@ -35,6 +35,7 @@ constexpr int kMaxPoints = 8;
 // msda_bwd_coarse.cu: a level with at most kCoarseCapRows pixels has its grad_value plane accumulated in shared
 // memory (128 B per row; 25x42 = 1 050 rows of the 800x1333 pyramid is the design point), one CTA per SM; planes of
 // at most kCoarseSmallRows (13x21 = 273) run several CTAs per SM.
+constexpr int kBf16ScatterDefault = 100;  // see rdetr_msda_set_bf16_scatter (include/rdetr_ops.h)
 constexpr int kCoarseCapRows = 1056;
 constexpr int kCoarseSmallRows = 280;
 
@@ -296,6 +297,19 @@ __device__ __forceinline__ bool coarse_level(int H, int W, int start, int S, int
 {
     const long long rows = (long long)H * W;
     return cap_rows > 0 && H > 0 && W > 0 && rows <= cap_rows && start >= 0 && start + rows <= S;
+}
+
+// bf16 backward: a level whose rows receive few updates (Nq*P*4 corners spread over H*W rows <= max_updates each, on
+// average) is scattered straight into the bf16 grad_value with packed bf16x2 reductions -- 64 bytes per row instead of
+// 128, 81 vs 48 G rows/s at the L2 (profiles/r02al_microbench_red.txt) -- instead of into the fp32 workspace.
+__device__ __forceinline__ bool direct_bf16_level(int H, int W, int Nq, int P, int max_updates)
+{
+    return max_updates > 0 && H > 0 && W > 0 && (long long)Nq * P * 4 <= (long long)max_updates * H * W;
+}
+// {a, b, c, d} added to four consecutive bf16 (8 bytes per lane, 8 lanes = one 64-byte row)
+__device__ __forceinline__ void red_add_bf16x4(__nv_bfloat16 *p, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1,%2};" ::"l"(p), "r"(pack_bf16(a, b)), "r"(pack_bf16(c, d)) : "memory");
 }
 
 // Walks the sample ids s = tid, tid + T, tid + 2T, ... of a CTA and keeps (pair, lp) = (s / LP, s % LP) up to

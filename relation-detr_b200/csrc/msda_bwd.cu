@@ -7,21 +7,22 @@
 // Same work layout as the forward (see msda_fwd.cu):
 //   * phase 1, one thread per sample: corner pixel indices, fractional offsets and the attention
 //     weight staged in shared memory (32 B per sample);
-//   * phase 2, 4 channels per lane, 8 lanes per (b,q,m) for fp32 AND bf16 (so that every lane's
-//     reduction is a full 16-byte fp32 vector and every corner one 128-byte request: the L2 atomic
-//     unit is request-rate bound, measured in profiles/): re-gather the four corners,
-//       - grad_value: one vector reduction (red.global.add.v4.f32, 16 B per lane => a whole
-//         128-byte row per corner for fp32) instead of 32 scalar atomics;
-//       - grad_attn / grad_loc: per-lane partial dot products over its channels, combined with
-//         log2(kLanes) xor-shuffles; the results overwrite the sample's shared-memory slot;
+//   * phase 2, 4 channels per lane, 8 lanes per (b,q,m) for fp32 AND bf16 (every corner is one request to the L2: the
+//     L2 charges per request and per 32-byte sector, profiles/r02al_microbench_red.txt): re-gather the four corners,
+//       - grad_value: one vector reduction per lane and corner instead of 32 scalar atomics -- red.global.add.v4.f32
+//         (a whole 128-byte fp32 row), or, for the fine levels of a bf16 call, red.global.add.noftz.v2.bf16x2 straight
+//         into the bf16 output (a 64-byte row: 1.69x the row rate; rdetr_msda_set_bf16_scatter);
+//       - grad_attn / grad_loc: per corner the lane forms <grad_out, value_i> over its channels; the four partials are
+//         reduced over the pair's lanes by a transposing butterfly (4 shuffles) and parked in the sample's shared-memory
+//         slot; the bilinear algebra on top of them is linear, so it runs once per sample in phase 3;
 //   * phase 3: grad_loc / grad_attn leave the CTA as dense, coalesced stores (every element is
 //     written, so the caller does not have to zero them; the reference zero-fills and then
 //     overwrites, ms_deform_attn_cuda.cu:113-115).
-// grad_value accumulates in fp32.  For bf16 value the accumulation target is an fp32 workspace that
-// a second kernel converts (bf16 accumulation would lose the small addends on coarse levels, where
-// one address receives ~1e3 updates).
+// grad_value accumulates in fp32.  For bf16 value the accumulation target of the coarse levels is an fp32 workspace that
+// a second kernel converts (bf16 accumulation would lose the small addends where one address receives ~1e3 updates).
 #include <atomic>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -43,12 +44,27 @@ int fork_coarse(const int64_t *shapes, const int64_t *lsi, const IO &io, const v
                 int L, int Nq, int P, cudaStream_t main, cudaStream_t *side_out, cudaEvent_t *done_out);
 int join_coarse(cudaStream_t main, cudaEvent_t done);
 
+// bf16 backward: average updates per grad_value row up to which a level is scattered with packed bf16x2 reductions
+// straight into grad_value (0: never; rdetr_msda_set_bf16_scatter / RDETR_MSDA_BF16_SCATTER)
+static std::atomic<int> g_bf16_scatter{-1};
+static int msda_bf16_scatter_max_updates()
+{
+    int v = g_bf16_scatter.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("RDETR_MSDA_BF16_SCATTER");
+        v = e ? atoi(e) : kBf16ScatterDefault;
+        if (v < 0) v = 0;
+        g_bf16_scatter.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 template <typename VT, int CH, int D, typename IO, int THREADS, int MINB = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatial_shapes,
                 const int64_t *__restrict__ level_start_index, const IO io, const VT *__restrict__ grad_out,
                 float *__restrict__ grad_value_f32, int S, int M, int L, int Nq, int P, long long total_pairs,
-                int coarse_cap_rows)
+                int coarse_cap_rows, VT *__restrict__ grad_value_direct, int direct_max_updates)
 {
     using SL = Slice<VT, CH>;
     constexpr int kCh = CH;
@@ -60,7 +76,8 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     __shared__ int s_H[kMaxLevels], s_W[kMaxLevels], s_start[kMaxLevels];
     __shared__ float s_invW[kMaxLevels], s_invH[kMaxLevels];
     __shared__ unsigned char s_lvl[kMaxLevels * kMaxPoints];  // level of sample slot lp (= lp / P)
-    __shared__ unsigned char s_scatter[kMaxLevels];           // 0: the level's grad_value is accumulated by msda_bwd_coarse_kernel
+    __shared__ unsigned char s_scatter[kMaxLevels];           // 0: the level's grad_value is accumulated by msda_bwd_coarse_kernel,
+                                                              // 1: fp32 reductions, 2: bf16x2 reductions straight into grad_value
     __shared__ long long s_bq[THREADS / (D / CH)];  // FusedIO: b*Nq + q of every pair (64-bit division once per pair, not per sample)
     __shared__ int s_b[THREADS / (D / CH)];
     const float inv_P = 1.0f / (float)P;
@@ -76,7 +93,11 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_start[threadIdx.x] = (int)level_start_index[threadIdx.x];
         s_invW[threadIdx.x] = 1.0f / (float)s_W[threadIdx.x];
         s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
-        s_scatter[threadIdx.x] = !coarse_level(s_H[threadIdx.x], s_W[threadIdx.x], s_start[threadIdx.x], S, coarse_cap_rows);
+        int mode = !coarse_level(s_H[threadIdx.x], s_W[threadIdx.x], s_start[threadIdx.x], S, coarse_cap_rows);
+        if (sizeof(VT) == 2 && mode && grad_value_direct != nullptr &&
+            direct_bf16_level(s_H[threadIdx.x], s_W[threadIdx.x], Nq, P, direct_max_updates))
+            mode = 2;
+        s_scatter[threadIdx.x] = (unsigned char)mode;
     }
     for (int i = threadIdx.x; i < L * P; i += THREADS) s_lvl[i] = (unsigned char)(i / P);
     __syncthreads();
@@ -120,6 +141,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     const long long batch_off = (b * S * M + m) * (long long)D + lane * kCh;
     const VT *vbase = value + batch_off;
     float *gvbase = grad_value_f32 + batch_off;
+    VT *gdbase = grad_value_direct + batch_off;  // only dereferenced for levels in mode 2
 
     float g[kCh];
 #pragma unroll
@@ -130,8 +152,10 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     float4 *my_meta = s_meta + pair * stride;
     const bool odd1 = lane & 1, odd2 = lane & 2;
     const int dot_slot = ((lane & 1) << 1) | ((lane >> 1) & 1);  // lanes 0..3 of the pair end up with d0, d2, d1, d3
-    for (int l = 0, lp = 0; l < L; ++l) {
-        const bool scatter = s_scatter[l] != 0;  // else: grad_value of this level comes from msda_bwd_coarse_kernel
+    // one level's P samples; MODE (compile time) = where the level's grad_value goes: 0 nowhere (msda_bwd_coarse_kernel
+    // accumulates it), 1 fp32 reductions into grad_value_f32, 2 packed bf16x2 reductions straight into grad_value
+    auto level_loop = [&](auto mode_c, int lp) {
+        constexpr int scatter = decltype(mode_c)::value;
 #pragma unroll 2
         for (int p = 0; p < P; ++p, ++lp) {
             const int4 px = my_pix[lp];
@@ -145,11 +169,18 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 SL::load(elem_ptr(vbase, px.y), v1);
                 SL::load(elem_ptr(vbase, px.z), v2);
                 SL::load(elem_ptr(vbase, px.w), v3);
-                if (scatter) {
+                if constexpr (scatter == 1) {
                     red_row<kCh>(elem_ptr(gvbase, px.x), w0, g);
                     red_row<kCh>(elem_ptr(gvbase, px.y), w1, g);
                     red_row<kCh>(elem_ptr(gvbase, px.z), w2, g);
                     red_row<kCh>(elem_ptr(gvbase, px.w), w3, g);
+                } else if constexpr (scatter == 2) {
+                    if constexpr (sizeof(VT) == 2 && kCh == 4) {
+                        red_add_bf16x4(elem_ptr(gdbase, px.x), w0 * g[0], w0 * g[1], w0 * g[2], w0 * g[3]);
+                        red_add_bf16x4(elem_ptr(gdbase, px.y), w1 * g[0], w1 * g[1], w1 * g[2], w1 * g[3]);
+                        red_add_bf16x4(elem_ptr(gdbase, px.z), w2 * g[0], w2 * g[1], w2 * g[2], w2 * g[3]);
+                        red_add_bf16x4(elem_ptr(gdbase, px.w), w3 * g[0], w3 * g[1], w3 * g[2], w3 * g[3]);
+                    }
                 }
             } else {
 #pragma unroll
@@ -158,11 +189,18 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
                 if (px.y >= 0) SL::load(elem_ptr(vbase, px.y), v1);
                 if (px.z >= 0) SL::load(elem_ptr(vbase, px.z), v2);
                 if (px.w >= 0) SL::load(elem_ptr(vbase, px.w), v3);
-                if (scatter) {
+                if constexpr (scatter == 1) {
                     if (px.x >= 0) red_row<kCh>(elem_ptr(gvbase, px.x), w0, g);
                     if (px.y >= 0) red_row<kCh>(elem_ptr(gvbase, px.y), w1, g);
                     if (px.z >= 0) red_row<kCh>(elem_ptr(gvbase, px.z), w2, g);
                     if (px.w >= 0) red_row<kCh>(elem_ptr(gvbase, px.w), w3, g);
+                } else if constexpr (scatter == 2) {
+                    if constexpr (sizeof(VT) == 2 && kCh == 4) {
+                        if (px.x >= 0) red_add_bf16x4(elem_ptr(gdbase, px.x), w0 * g[0], w0 * g[1], w0 * g[2], w0 * g[3]);
+                        if (px.y >= 0) red_add_bf16x4(elem_ptr(gdbase, px.y), w1 * g[0], w1 * g[1], w1 * g[2], w1 * g[3]);
+                        if (px.z >= 0) red_add_bf16x4(elem_ptr(gdbase, px.z), w2 * g[0], w2 * g[1], w2 * g[2], w2 * g[3]);
+                        if (px.w >= 0) red_add_bf16x4(elem_ptr(gdbase, px.w), w3 * g[0], w3 * g[1], w3 * g[2], w3 * g[3]);
+                    }
                 }
             }
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
@@ -185,6 +223,12 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
             // the pixel slot is dead after this iteration: it receives (d0, d1, d2, d3)
             if (lane < 4) reinterpret_cast<float *>(const_cast<int4 *>(my_pix + lp))[dot_slot] = z;
         }
+    };
+    for (int l = 0, lp = 0; l < L; ++l, lp += P) {
+        const int scatter = s_scatter[l];
+        if (scatter == 1) level_loop(std::integral_constant<int, 1>{}, lp);
+        else if (sizeof(VT) == 2 && scatter == 2) level_loop(std::integral_constant<int, 2>{}, lp);
+        else level_loop(std::integral_constant<int, 0>{}, lp);
     }
     __syncthreads();
 
@@ -260,12 +304,36 @@ __global__ void spin_kernel(long long ns)
     }
 }
 
-// fp32 accumulation buffer -> bf16 grad_value (8 elements per thread)
+// fp32 accumulation buffer -> bf16 grad_value (8 elements per thread).  Rows of levels that were scattered straight into
+// grad_value (mode 2 of msda_bwd_kernel: direct_max_updates > 0) are left alone; everything else is overwritten.
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
-                                                          long long n8)
+                                                          long long n8, const int64_t *__restrict__ spatial_shapes,
+                                                          const int64_t *__restrict__ level_start_index, int L, int S, int M, int Nq,
+                                                          int P, int coarse_cap_rows, int direct_max_updates)
 {
+    __shared__ int s_lo[kMaxLevels], s_hi[kMaxLevels];  // row ranges of the directly scattered levels (empty: lo = hi = 0)
+    if (threadIdx.x < kMaxLevels) {
+        int lo = 0, hi = 0;
+        if (direct_max_updates > 0 && (int)threadIdx.x < L) {
+            const int H = (int)spatial_shapes[2 * threadIdx.x], W = (int)spatial_shapes[2 * threadIdx.x + 1];
+            const int start = (int)level_start_index[threadIdx.x];
+            if (!coarse_level(H, W, start, S, coarse_cap_rows) && direct_bf16_level(H, W, Nq, P, direct_max_updates)) {
+                lo = start;
+                hi = start + H * W;
+            }
+        }
+        s_lo[threadIdx.x] = lo;
+        s_hi[threadIdx.x] = hi;
+    }
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n8) return;
+    if (direct_max_updates > 0) {
+        const int row = (int)((i * 8 / ((long long)M * 32)) % S);
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l)
+            if (row >= s_lo[l] && row < s_hi[l]) return;
+    }
     const float4 a = ld_stream_f4(reinterpret_cast<const float4 *>(src) + 2 * i);
     const float4 b = ld_stream_f4(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
     uint4 t;
@@ -276,7 +344,8 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
 
 template <typename VT, int CH, typename IO, int THREADS, int MINB = 0>
 static int launch_bwd_variant(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
-                              float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, cudaStream_t stream)
+                              float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, void *gv_direct,
+                              int direct_max, cudaStream_t stream)
 {
     constexpr int D = 32;
     constexpr int kLanes = D / CH;
@@ -308,13 +377,15 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
     const long long grid = (total_pairs + kPairs - 1) / kPairs;
     if (grid > 0x7fffffffLL) return fail(RDETR_ERR_UNSUPPORTED, "msda_backward: B*Nq*M too large (%lld pairs)", total_pairs);
     kern<<<(unsigned)grid, THREADS, smem, stream>>>(static_cast<const VT *>(value), shapes, lsi, io,
-                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs, coarse_cap);
+                                                    static_cast<const VT *>(grad_out), gv_f32, S, M, L, Nq, P, total_pairs, coarse_cap,
+                                                    static_cast<VT *>(gv_direct), direct_max);
     return check_cuda(cudaGetLastError(), "msda_bwd_kernel launch");
 }
 
 template <typename VT, int CH, typename IO>
 static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *lsi, const IO &io, const void *grad_out,
-                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, cudaStream_t stream)
+                      float *gv_f32, int B, int S, int M, int L, int Nq, int P, int coarse_cap, void *gv_direct, int direct_max,
+                      cudaStream_t stream)
 {
     // encoder self-attention (every query is a pixel of the pyramid): tiled kernel with shared-memory grad_value
     // accumulators (msda_bwd_tile.cu); rdetr_msda_set_tile_mode(1) / RDETR_MSDA_TILE=1 keeps the flat kernel
@@ -325,19 +396,19 @@ static int launch_bwd(const void *value, const int64_t *shapes, const int64_t *l
 #ifdef RDETR_TUNE_FWD
     const char *e = getenv("RDETR_MSDA_BWD_VARIANT");
     const int v = e ? atoi(e) : 0;
-    if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
-    if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
-    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 10>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    if (v == 1) return launch_bwd_variant<VT, CH, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
+    if (v == 2) return launch_bwd_variant<VT, CH, IO, 64>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
+    if (v == 3) return launch_bwd_variant<VT, CH, IO, 128, 10>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
     if constexpr (sizeof(VT) == 4) {
-        if (v == 5) return launch_bwd_variant<VT, 2, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
-        if (v == 6) return launch_bwd_variant<VT, 2, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
-        if (v == 7) return launch_bwd_variant<VT, 2, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+        if (v == 5) return launch_bwd_variant<VT, 2, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
+        if (v == 6) return launch_bwd_variant<VT, 2, IO, 256>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
+        if (v == 7) return launch_bwd_variant<VT, 2, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
     }
-    if (v == 4) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    if (v == 4) return launch_bwd_variant<VT, CH, IO, 128, 12>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
 #endif
     // 128 threads: within noise of 256 / 64 (the kernel is L2-atomic bound), fewest barrier stalls; register
     // caps for more occupancy spill and are 30-70 % slower (variant 3)
-    return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, stream);
+    return launch_bwd_variant<VT, CH, IO, 128>(value, shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, coarse_cap, gv_direct, direct_max, stream);
 }
 
 // zero-fill of the fp32 accumulation target, the scatter kernel, and (bf16) the final conversion
@@ -349,9 +420,16 @@ static int run_backward(const void *value, const int64_t *shapes, const int64_t 
     const size_t nvalue = (size_t)B * S * M * D;
     float *acc = dtype == RDETR_DTYPE_F32 ? static_cast<float *>(grad_value) : static_cast<float *>(workspace);
     if (int rc = check_cuda(cudaMemsetAsync(acc, 0, nvalue * sizeof(float), st), "cudaMemsetAsync(grad_value)")) return rc;
+    const bool tiled = Nq == S && msda_tile_mode() == 2;
+    // bf16: levels whose rows receive few updates are scattered straight into the (zeroed) bf16 grad_value
+    const int direct_max = (dtype == RDETR_DTYPE_BF16 && !tiled && Nq > 0) ? msda_bf16_scatter_max_updates() : 0;
+    void *gv_direct = direct_max > 0 ? grad_value : nullptr;
+    if (direct_max > 0)
+        if (int rc = check_cuda(cudaMemsetAsync(grad_value, 0, nvalue * sizeof(__nv_bfloat16), st), "cudaMemsetAsync(grad_value bf16)")) return rc;
+    int cap = 0;
     if (Nq > 0) {
         // coarse levels: shared-memory accumulation on a side stream, concurrent with the scatter kernel (msda_bwd_coarse.cu)
-        const int cap = (Nq == S && msda_tile_mode() == 2) ? 0 : msda_coarse_cap_rows(Nq, P);
+        cap = tiled ? 0 : msda_coarse_cap_rows(Nq, P);
         cudaStream_t side = nullptr;
         cudaEvent_t done = nullptr;
         if (cap > 0) {
@@ -366,8 +444,9 @@ static int run_backward(const void *value, const int64_t *shapes, const int64_t 
         if (cap > 0 && exp_delay_us > 0) spin_kernel<<<1, 32, 0, st>>>(exp_delay_us * 1000LL);
         if (!(cap > 0 && exp_skip_scatter))
         rc = dtype == RDETR_DTYPE_F32
-                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, cap, st)
-                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, cap, st);
+                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, cap, nullptr, 0, st)
+                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, cap, gv_direct,
+                                                          direct_max, st);
         if (cap > 0) {
             const int rj = join_coarse(st, done);
             if (rc == RDETR_OK && rj) return rj;
@@ -376,7 +455,8 @@ static int run_backward(const void *value, const int64_t *shapes, const int64_t 
     }
     if (dtype == RDETR_DTYPE_BF16) {
         const long long n8 = (long long)(nvalue / 8);  // D == 32 => divisible
-        f32_to_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(acc, static_cast<__nv_bfloat16 *>(grad_value), n8);
+        f32_to_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(acc, static_cast<__nv_bfloat16 *>(grad_value), n8, shapes, lsi, L, S,
+                                                                         M, Nq, P, cap, direct_max);
         return check_cuda(cudaGetLastError(), "f32_to_bf16_kernel launch");
     }
     return RDETR_OK;
@@ -452,4 +532,12 @@ extern "C" int rdetr_msda_fused_backward(const void *value, const int64_t *spati
                                       static_cast<__nv_bfloat16 *>(grad_offsets), static_cast<__nv_bfloat16 *>(grad_logits), ref_dim};
     return run_backward(value, spatial_shapes, level_start_index, io32, io16, grad_out, grad_value, B, S, M, D, L, Nq, P, dtype,
                         workspace, st);
+}
+
+extern "C" int rdetr_msda_set_bf16_scatter(int max_updates_per_row)
+{
+    if (max_updates_per_row < 0)
+        return rdetr::fail(RDETR_ERR_INVALID_ARGUMENT, "rdetr_msda_set_bf16_scatter: max_updates_per_row must be >= 0, got %d", max_updates_per_row);
+    rdetr::g_bf16_scatter.store(max_updates_per_row, std::memory_order_relaxed);
+    return RDETR_OK;
 }
