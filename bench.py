@@ -742,7 +742,12 @@ def run_ours(args):
             d2 = workloads.make_msda_inputs(shape_, kind, seed=0, device=dev)
             t, f, b = time_msda(torch, ops, d2, k, w, dt)
             fb2, bb2 = shape_.algorithmic_bytes(nbytes)
-            return {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((fb2 + bb2) / t / 1e6, 1)}
+            r = {"ms": round(t, 4), "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "GBps": round((fb2 + bb2) / t / 1e6, 1)}
+            if dt == torch.bfloat16:
+                r["frac_of_hbm"] = round((fb2 + bb2) / t / 1e6 / measured_peak()[0], 4)
+                r["grad_value_scatter"] = ("levels with <= %s updates per row on average: packed bf16x2 reductions straight into grad_value, "
+                                           "the rest: fp32 workspace (rdetr_msda_set_bf16_scatter)" % os.environ.get("RDETR_MSDA_BF16_SCATTER", "100"))
+            return r
 
         other = "U" if args.loc == "S" else "S"
         guarded(f"msda_enc_b8_f32_loc{other}", lambda: msda_variant(shape, other, torch.float32, 4))
