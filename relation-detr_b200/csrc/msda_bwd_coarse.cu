@@ -22,6 +22,7 @@
 // The kernel runs on a side stream next to the scatter kernel (which skips these levels): it needs issue slots and
 // shared-memory bandwidth, the scatter kernel needs L2 reduction throughput.  Which levels it takes is decided on the
 // device from spatial_shapes (coarse_level() in common.cuh) -- the shape tensors never visit the host.
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
