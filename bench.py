@@ -273,7 +273,7 @@ def time_e2e(torch, rd, inp, steps, warmup):
     dev = inp["value"].device
     host = {k: inp[k].cpu().pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
     pipe = MsdaHostPipeline(inp["spatial_shapes"], inp["level_start_index"], dev)
-    for _ in range(max(warmup, 2)):
+    for _ in range(max(warmup, pipe.depth + 2)):   # fills every slot and lets the caching allocator reach its steady state
         pipe.submit(host)
     pipe.wait()
     torch.cuda.synchronize()
@@ -817,6 +817,11 @@ def run_ours(args):
                          "fwd_kernel": {"achieved": round(fwd_b / fwd_max / 1e6, 1), "frac": round(fwd_b / fwd_max / 1e6 / peak, 4), "ms": round(fwd_max, 4)},
                          "bwd_ms": round(bwd_max, 4), "fwd_bwd_frac": round(value / world / peak, 4), "rel": rel_roof,
                          "memory_fusion": (extra.get("memory_fusion_b8") or {}).get("roofline") if isinstance(extra.get("memory_fusion_b8"), dict) else None,
+                         # the same workload with bf16 value / out / grad_out / grad_value (1 280 MB algorithmic); None under --quick
+                         "msda_bf16": (extra.get(f"msda_enc_b8_bf16_loc{args.loc}") if isinstance(extra.get(f"msda_enc_b8_bf16_loc{args.loc}"), dict)
+                                       and "error" not in extra.get(f"msda_enc_b8_bf16_loc{args.loc}") else None),
+                         "floor_note": "with the grad_value reductions removed level by level the backward takes 1.775 / 1.587 / 1.379 / 1.153 / 0.892 ms "
+                                       "(profiles/r02aa_exp_lean.txt): 0.58 + 0.89 ms = 18 % of HBM is the floor of any kernel that touches one 128-byte row per bilinear corner",
                          # the resources that actually bind: one 128-byte row per bilinear corner
                          "binding": {
                              "corner_rows_per_launch": corner_rows,

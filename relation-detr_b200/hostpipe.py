@@ -2,8 +2,10 @@
 
 The hot path is 2.5 ms of GPU work per batch but 640 MB in and 640 MB out over PCIe, so a caller whose
 tensors live in host memory is transfer-bound.  ``MsdaHostPipeline`` keeps three CUDA streams busy
-(copy-in of step i+1, compute of step i, copy-out of step i-1) with double-buffered device inputs and
-pinned host outputs, at most ``depth`` steps in flight; every step still copies all of its inputs in and all of its results out.  The
+(copy-in of step i+1, compute of step i, copy-out of step i-1) with ``depth`` device input buffers and
+pinned host output buffers, at most ``depth`` steps in flight (default 3: with two, the copy-in of step i waits for the
+copy-out of step i-2, which makes the period (copy-in + compute + copy-out) / 2 = 14.7 ms at configs[1] instead of the
+slower copy's 14.0 ms -- profiles/r02ah_exp_e2e_depth.txt); every step still copies all of its inputs in and all of its results out.  The
 compute goes through the public operator (``MultiScaleDeformableAttnFunction.apply`` + autograd).
 """
 from __future__ import annotations
@@ -19,7 +21,7 @@ _OUT_KEYS = ("out", "grad_value", "grad_loc", "grad_attn")
 
 
 class MsdaHostPipeline:
-    def __init__(self, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor, device, depth: int = 2):
+    def __init__(self, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor, device, depth: int = 3):
         self.device = torch.device(device)
         self.ss = spatial_shapes.to(self.device)
         self.lsi = level_start_index.to(self.device)

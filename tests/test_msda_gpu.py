@@ -271,21 +271,22 @@ def test_module_matches_torch_port_pipeline():
     assert ob.dtype == torch.bfloat16 and (ob.float() - out).abs().max().item() <= 0.1
 
 
-def test_host_pipeline_matches_direct_call():
+@pytest.mark.parametrize("depth", [2, 3])
+def test_host_pipeline_matches_direct_call(depth):
     """hostpipe.MsdaHostPipeline (H2D -> op -> D2H on three streams) returns what the direct call returns,
     for several steps in flight with different inputs."""
     from relation_detr_b200.hostpipe import MsdaHostPipeline
 
     shape = workloads.MsdaShape("t", 2, ((25, 42), (13, 21), (7, 11), (4, 6)), 300)
     ss, lsi = workloads.shape_tensors(shape.levels)
-    pipe = MsdaHostPipeline(ss, lsi, DEV)
+    pipe = MsdaHostPipeline(ss, lsi, DEV, depth=depth)
     batches, results = [], []
     for seed in range(5):
         inp = workloads.make_msda_inputs(shape, "oob", seed=seed)
         host = {k: inp[k].pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_output")}
         batches.append(inp)
         res = pipe.submit(host)
-        if seed >= 3:  # buffers are recycled with depth 2: read back the last two only after wait()
+        if seed >= 3:  # buffers are recycled after `depth` (2 or 3) submits: read back the last two only after wait()
             results.append((seed, res))
     pipe.wait()
     for seed, res in results:
