@@ -95,7 +95,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
         s_invH[threadIdx.x] = 1.0f / (float)s_H[threadIdx.x];
         int mode = !coarse_level(s_H[threadIdx.x], s_W[threadIdx.x], s_start[threadIdx.x], S, coarse_cap_rows);
         if (sizeof(VT) == 2 && mode && grad_value_direct != nullptr &&
-            direct_bf16_level(s_H[threadIdx.x], s_W[threadIdx.x], Nq, P, direct_max_updates))
+            direct_bf16_level(s_H[threadIdx.x], s_W[threadIdx.x], Nq, P, direct_max_updates, S))
             mode = 2;
         s_scatter[threadIdx.x] = (unsigned char)mode;
     }
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
         if (direct_max_updates > 0 && (int)threadIdx.x < L) {
             const int H = (int)spatial_shapes[2 * threadIdx.x], W = (int)spatial_shapes[2 * threadIdx.x + 1];
             const int start = (int)level_start_index[threadIdx.x];
-            if (!coarse_level(H, W, start, S, coarse_cap_rows) && direct_bf16_level(H, W, Nq, P, direct_max_updates)) {
+            if (!coarse_level(H, W, start, S, coarse_cap_rows) && direct_bf16_level(H, W, Nq, P, direct_max_updates, S)) {
                 lo = start;
                 hi = start + H * W;
             }
