@@ -122,8 +122,10 @@ int rdetr_msda_set_coarse_mode(int mode);
  * bf16 accumulation would swallow).  Every addition then rounds to bf16: the directly scattered rows carry about
  * sqrt(updates) * 2^-9 relative error instead of the final rounding's 2^-9 (tests/test_msda_bf16_scatter_gpu.py bounds it
  * level by level).  Default 100: the two finest levels of an encoder call, bf16 backward 1.75 -> 1.47 ms at configs[1]
- * (profiles/r02an_exp_bf16_scatter.txt); 0 = never (also RDETR_MSDA_BF16_SCATTER in the environment).  Process-wide,
- * safe to call from any thread.  fp32 calls are unaffected.
+ * (profiles/r02an_exp_bf16_scatter.txt); 0 = never (also RDETR_MSDA_BF16_SCATTER in the environment).  The criterion is
+ * an average: an input that sends most of its samples to a few rows of a fine level (nothing a detector produces, but
+ * possible) loses accuracy on those rows -- use 0 for such inputs.  Process-wide, safe to call from any thread.  fp32
+ * calls are unaffected.
  */
 int rdetr_msda_set_bf16_scatter(int max_updates_per_row);
 
