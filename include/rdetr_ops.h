@@ -116,7 +116,7 @@ int rdetr_msda_set_coarse_mode(int mode);
  * Backward with bf16 value only.  A pyramid level whose grad_value rows receive at most `max_updates_per_row` updates
  * on average (Nq * P * 4 bilinear corners over H * W rows: 21 for the finest level of both shipped pyramids when
  * Nq = S, 85 for the next; a quarter of the limit applies when Nq != S, where queries cluster on objects and the
- * average under-states the busiest rows) is scattered straight into the bf16 grad_value with packed bf16x2 vector reductions
+ * average under-states the busiest rows; levels of fewer than 1 024 pixels never qualify) is scattered straight into the bf16 grad_value with packed bf16x2 vector reductions
  * (64 bytes per row: 81 G rows/s at the L2 against 48 G rows/s for 128-byte fp32 rows, profiles/r02al_microbench_red.txt)
  * instead of into the fp32 workspace; the other levels keep fp32 accumulation (a coarse row receives ~1e3 updates, which
  * bf16 accumulation would swallow).  Every addition then rounds to bf16: the directly scattered rows carry about

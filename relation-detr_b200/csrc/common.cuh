@@ -303,11 +303,15 @@ __device__ __forceinline__ bool coarse_level(int H, int W, int start, int S, int
 // average) is scattered straight into the bf16 grad_value with packed bf16x2 reductions -- 64 bytes per row instead of
 // 128, 81 vs 48 G rows/s at the L2 (profiles/r02al_microbench_red.txt) -- instead of into the fp32 workspace.
 // The average is representative when every pixel of the pyramid is a query (Nq == S: encoder self-attention); the queries
-// of a decoder call cluster on objects, so a quarter of the limit is applied there.
+// of a decoder call cluster on objects, so a quarter of the limit is applied there.  Levels of fewer than
+// kBf16ScatterMinRows pixels never qualify: on a small level the in-range samples pile up on a few rows (the average says
+// little) and there is nothing to gain.
+constexpr int kBf16ScatterMinRows = 1024;
 __device__ __forceinline__ bool direct_bf16_level(int H, int W, int Nq, int P, int max_updates, int S)
 {
     const long long lim = Nq == S ? max_updates : max_updates / 4;
-    return lim > 0 && H > 0 && W > 0 && (long long)Nq * P * 4 <= lim * H * W;
+    const long long rows = (long long)H * W;
+    return lim > 0 && H > 0 && W > 0 && rows >= kBf16ScatterMinRows && (long long)Nq * P * 4 <= lim * rows;
 }
 // {a, b, c, d} added to four consecutive bf16 (8 bytes per lane, 8 lanes = one 64-byte row)
 __device__ __forceinline__ void red_add_bf16x4(__nv_bfloat16 *p, float a, float b, float c, float d)

@@ -292,6 +292,7 @@ msda_bwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ spatia
     }
 }
 
+#ifdef RDETR_TUNE_FWD
 __global__ void spin_kernel(long long ns)
 {
     long long t0;
@@ -303,6 +304,7 @@ __global__ void spin_kernel(long long ns)
         __nanosleep(200);
     }
 }
+#endif
 
 // fp32 accumulation buffer -> bf16 grad_value (8 elements per thread).  Rows of levels that were scattered straight into
 // grad_value (mode 2 of msda_bwd_kernel: direct_max_updates > 0) are left alone; everything else is overwritten.
@@ -364,7 +366,11 @@ static int launch_bwd_variant(const void *value, const int64_t *shapes, const in
     // next to the coarse kernel (which needs the largest shared-memory carve-out) the scatter kernel asks for the same
     // L1 / shared split: an SM does not hold CTAs of two kernels that want different splits.  Set only when it changes.
     {
+#ifdef RDETR_TUNE_FWD
         static const int exp_carve = getenv("RDETR_COARSE_CARVEOUT") ? atoi(getenv("RDETR_COARSE_CARVEOUT")) : 1;
+#else
+        constexpr int exp_carve = 1;
+#endif
         static std::atomic<int> current{(int)cudaSharedmemCarveoutDefault};  // per instantiation of this template
         const int want = (coarse_cap > 0 && exp_carve) ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault;
         if (current.load(std::memory_order_relaxed) != want) {
@@ -439,14 +445,19 @@ static int run_backward(const void *value, const int64_t *shapes, const int64_t 
             if (rc) return rc;
         }
         int rc = RDETR_OK;
-        static const int exp_delay_us = getenv("RDETR_COARSE_DELAY_US") ? atoi(getenv("RDETR_COARSE_DELAY_US")) : 0;  // experiments
+        bool skip_scatter = false;
+#ifdef RDETR_TUNE_FWD
+        // tuning builds only (tools/exp_coarse2.py): hold the scatter kernel back so that the coarse CTAs are resident first,
+        // or leave it out altogether (wrong gradients: timing of the coarse kernel alone)
+        static const int exp_delay_us = getenv("RDETR_COARSE_DELAY_US") ? atoi(getenv("RDETR_COARSE_DELAY_US")) : 0;
         static const int exp_skip_scatter = getenv("RDETR_COARSE_ONLY") ? atoi(getenv("RDETR_COARSE_ONLY")) : 0;
         if (cap > 0 && exp_delay_us > 0) spin_kernel<<<1, 32, 0, st>>>(exp_delay_us * 1000LL);
-        if (!(cap > 0 && exp_skip_scatter))
-        rc = dtype == RDETR_DTYPE_F32
-                           ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, cap, nullptr, 0, st)
-                           : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, cap, gv_direct,
-                                                          direct_max, st);
+        skip_scatter = cap > 0 && exp_skip_scatter;
+#endif
+        if (!skip_scatter)
+            rc = dtype == RDETR_DTYPE_F32
+                     ? launch_bwd<float, 4>(value, shapes, lsi, io32, grad_out, acc, B, S, M, L, Nq, P, cap, nullptr, 0, st)
+                     : launch_bwd<__nv_bfloat16, 4>(value, shapes, lsi, io16, grad_out, acc, B, S, M, L, Nq, P, cap, gv_direct, direct_max, st);
         if (cap > 0) {
             const int rj = join_coarse(st, done);
             if (rc == RDETR_OK && rj) return rj;

@@ -367,8 +367,12 @@ int fork_coarse(const int64_t *shapes, const int64_t *lsi, const IO &io, const v
     int rc = check_cuda(cudaEventRecord(start, main), "cudaEventRecord");
     if (!rc) rc = check_cuda(cudaStreamWaitEvent(side, start, 0), "cudaStreamWaitEvent");
     // big planes first (one CTA per SM, the long pole), then the small ones (up to three per SM next to them)
-    // experiments (profiles/r02ac-r02ae_exp_coarse2.txt): 1 skips the big class, 2 the small one, 3 both
-    static const int exp_skip = getenv("RDETR_COARSE_SKIP") ? atoi(getenv("RDETR_COARSE_SKIP")) : 0;
+    int exp_skip = 0;
+#ifdef RDETR_TUNE_FWD
+    // tuning builds only (profiles/r02ac-r02ae_exp_coarse2.txt): 1 skips the big class, 2 the small one, 3 both
+    static const int exp_skip_env = getenv("RDETR_COARSE_SKIP") ? atoi(getenv("RDETR_COARSE_SKIP")) : 0;
+    exp_skip = exp_skip_env;
+#endif
     if (!rc && !(exp_skip & 1)) rc = launch_coarse_class<VT, IO>(shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, kCoarseSmallRows, kCoarseCapRows, 1, sms, side);
     if (!rc && !(exp_skip & 2)) rc = launch_coarse_class<VT, IO>(shapes, lsi, io, grad_out, gv_f32, B, S, M, L, Nq, P, 0, kCoarseSmallRows, 2, sms, side);
     if (!rc) rc = check_cuda(cudaEventRecord(done, side), "cudaEventRecord");

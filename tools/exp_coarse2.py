@@ -1,5 +1,11 @@
+"""Why the coarse-level kernel loses: each kernel alone, both, the scatter kernel held back, per level class.
+Needs the tuning build (the RDETR_COARSE_* knobs are compiled out of the shipped library):
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O2 -shared -DRDETR_TUNE_FWD \
+         -I include -I relation-detr_b200/csrc -o tools/librdetr_tune.so relation-detr_b200/csrc/*.cu
+"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tools", "librdetr_tune.so")
 code = r'''
 import os, sys, torch
 sys.path.insert(0, %r)
@@ -32,7 +38,7 @@ runs = [
     ("on, K1 delayed 50us, small only", {"RDETR_MSDA_COARSE": "2", "RDETR_COARSE_DELAY_US": "50", "RDETR_COARSE_SKIP": "1"}),
 ]
 for tag, extra in runs:
-    env = dict(os.environ, TAG=tag, **extra)
+    env = dict(os.environ, TAG=tag, RDETR_OPS_LIB=LIB, **extra)
     try:
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
         print(out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:], flush=True)
